@@ -1,0 +1,317 @@
+"""tests/golden/make_golden.py -- generates the committed fixtures in this directory.
+
+RUNS ONLY IN THE BUILD CONTAINER (it imports the reference from /root/reference, which
+does not exist on the GPU box).  The reference repository stores no golden vectors
+(src/models/ops/test.py only prints booleans), so the fixtures are outputs of the
+reference's own Python code executed here:
+
+  op_*.npz    ms_deform_attn_core_pytorch (functions/ms_deform_attn_func.py:102-122) forward
+              and torch-autograd backward, float64
+  mod_*.npz   the reference nn.Modules MSDeformAttn / TemporalMSDeformAttnEncoder /
+              TemporalMSDeformAttnDecoder (modules/ms_deform_attn.py) with
+              MSDeformAttnFunction's compiled backend replaced by the PyTorch core,
+              float64, including their state_dict
+  book_*.npz  the temporal bookkeeping tensors DeVISTransformerEncoder/Decoder hand to
+              their layers (devis_transformer.py:90-123,140-173)
+
+Usage:  python tests/golden/make_golden.py
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+# --------------------------------------------------------------------------------------
+# importing the reference without its heavy, missing dependencies
+# --------------------------------------------------------------------------------------
+def import_reference():
+    """Returns (func_module, modules_module, devis_transformer_module, deformable_transformer)."""
+    msda = types.ModuleType("MultiScaleDeformableAttention")
+    sys.modules["MultiScaleDeformableAttention"] = msda
+    visdom = types.ModuleType("visdom")
+    visdom.Visdom = object
+    sys.modules.setdefault("visdom", visdom)
+
+    def pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        m.__package__ = name
+        sys.modules[name] = m
+        return m
+
+    pkg("refsrc", f"{REF}/src")
+    pkg("refsrc.models", f"{REF}/src/models")          # skip models/__init__.py (pulls datasets etc.)
+    pkg("refsrc.util", f"{REF}/src/util")              # skip util/__init__.py
+    pkg("refsrc.models.ops", f"{REF}/src/models/ops")
+    func = importlib.import_module("refsrc.models.ops.functions.ms_deform_attn_func")
+    core = func.ms_deform_attn_core_pytorch
+
+    # the compiled backend, replaced by the reference's own PyTorch core + autograd
+    def fwd(value, shapes, lsi, loc, aw, step):
+        return core(value, shapes, loc, aw)
+
+    def bwd(value, shapes, lsi, loc, aw, grad_out, step):
+        with torch.enable_grad():
+            v = value.detach().requires_grad_(True)
+            l_ = loc.detach().requires_grad_(True)
+            a = aw.detach().requires_grad_(True)
+            out = core(v, shapes, l_, a)
+            return list(torch.autograd.grad(out, (v, l_, a), grad_out))
+
+    msda.ms_deform_attn_forward = fwd
+    msda.ms_deform_attn_backward = bwd
+    mods = importlib.import_module("refsrc.models.ops.modules.ms_deform_attn")
+    devis_tr = importlib.import_module("refsrc.models.devis_transformer")
+    def_tr = importlib.import_module("refsrc.models.deformable_transformer")
+    return func, mods, devis_tr, def_tr
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path)} bytes")
+
+
+def lsi_of(shapes):
+    return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+
+
+def safe_locations(gen, dims, shapes, lo=-0.12, hi=1.12):
+    """locations whose pixel coordinate keeps >=0.02 px distance from every integer, so the
+    floor() cell is identical for loc*W-0.5 (CUDA) and ((2loc-1+1)W-1)/2 (grid_sample);
+    about 10-20 % of the taps land outside the map (range check / zero padding paths)."""
+    n, lq, m, nl, p = dims
+    loc = torch.empty(n, lq, m, nl, p, 2, dtype=torch.float64)
+    for lvl, (h, w) in enumerate(shapes.tolist()):
+        for axis, size in ((0, w), (1, h)):
+            span = (hi - lo) * size
+            cell = torch.floor(torch.rand(n, lq, m, p, generator=gen, dtype=torch.float64) * span + lo * size)
+            frac = 0.02 + 0.96 * torch.rand(n, lq, m, p, generator=gen, dtype=torch.float64)
+            loc[:, :, :, lvl, :, axis] = (cell + frac + 0.5) / size
+    return loc
+
+
+# --------------------------------------------------------------------------------------
+# op-level fixtures
+# --------------------------------------------------------------------------------------
+def op_case(core, name, value, shapes, loc, aw, gout):
+    v = value.clone().requires_grad_(True)
+    l_ = loc.clone().requires_grad_(True)
+    a = aw.clone().requires_grad_(True)
+    out = core(v, shapes, l_, a)
+    gv, gl, ga = torch.autograd.grad(out, (v, l_, a), gout)
+    save(name, value=value, shapes=shapes, lsi=lsi_of(shapes), loc=loc, aw=aw, gout=gout,
+         out=out, gvalue=gv, gloc=gl, gaw=ga)
+
+
+def make_op_fixtures(func):
+    core = func.ms_deform_attn_core_pytorch
+    # 1. the reference test's own shape and seed (test.py:19-26,31-34), float64
+    torch.manual_seed(3)
+    n, m, d, lq, nl, p = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    s = int(shapes.prod(1).sum())
+    value = (torch.rand(n, s, m, d) * 0.01).double()
+    loc = torch.rand(n, lq, m, nl, p, 2).double()
+    aw = torch.rand(n, lq, m, nl, p).double() + 1e-5
+    aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    gout = torch.rand(n, lq, m * d).double()
+    op_case(core, "op_testpy", value, shapes, loc, aw, gout)
+
+    gen = torch.Generator().manual_seed(1234)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=gen, dtype=torch.float64)
+
+    # 2. ragged levels, batch 2, odd head/channel counts, taps outside the map
+    shapes = torch.as_tensor([(7, 9), (4, 5), (2, 3), (1, 1)], dtype=torch.long)
+    n, m, d, lq, nl, p = 2, 3, 8, 11, 4, 4
+    s = int(shapes.prod(1).sum())
+    loc = safe_locations(gen, (n, lq, m, nl, p), shapes, lo=-0.3, hi=1.3)
+    aw = torch.softmax(rnd(n, lq, m, nl * p), -1).view(n, lq, m, nl, p)
+    op_case(core, "op_ragged", rnd(n, s, m, d), shapes, loc, aw, rnd(n, lq, m * d))
+
+    # 3. the DeVIS head layout (8 heads x 32 channels) on a small pyramid
+    shapes = torch.as_tensor([(8, 12), (4, 6), (2, 3)], dtype=torch.long)
+    n, m, d, lq, nl, p = 1, 8, 32, 37, 3, 4
+    s = int(shapes.prod(1).sum())
+    loc = safe_locations(gen, (n, lq, m, nl, p), shapes)
+    aw = torch.softmax(rnd(n, lq, m, nl * p), -1).view(n, lq, m, nl, p)
+    op_case(core, "op_d32", rnd(n, s, m, d), shapes, loc, aw, rnd(n, lq, m * d))
+
+    # 4. channel counts off the fast paths (the reference sweeps 30/32/64/71/..., test.py:83)
+    shapes = torch.as_tensor([(5, 6), (3, 3)], dtype=torch.long)
+    for d in (1, 30, 71):
+        n, m, lq, nl, p = 1, 2, 5, 2, 3
+        s = int(shapes.prod(1).sum())
+        loc = safe_locations(gen, (n, lq, m, nl, p), shapes)
+        aw = torch.softmax(rnd(n, lq, m, nl * p), -1).view(n, lq, m, nl, p)
+        op_case(core, f"op_d{d}", rnd(n, s, m, d), shapes, loc, aw, rnd(n, lq, m * d))
+
+    # 5. border behaviour: taps on the last/first half pixel, just inside / outside the -1 < x < W test
+    shapes = torch.as_tensor([(4, 6)], dtype=torch.long)
+    n, m, d, nl, p = 1, 1, 4, 1, 1
+    xs = [-0.75, -0.25, 0.25, 2.6, 5.25, 5.75, 6.25, 6.6]      # pixel coordinate + 0.5 (i.e. loc*W)
+    ys = [-0.75, -0.25, 0.25, 1.7, 3.25, 3.75, 4.25, 4.6]
+    pts = [(x / 6.0, y / 4.0) for y in ys for x in xs]
+    lq = len(pts)
+    loc = torch.tensor(pts, dtype=torch.float64).view(n, lq, m, nl, p, 2)
+    aw = 0.5 + torch.rand(n, lq, m, nl, p, generator=gen, dtype=torch.float64)
+    op_case(core, "op_border", rnd(n, 24, m, d), shapes, loc, aw, rnd(n, lq, m * d))
+
+
+# --------------------------------------------------------------------------------------
+# module-level fixtures
+# --------------------------------------------------------------------------------------
+def randomize(module, gen):
+    with torch.no_grad():
+        for prm in module.parameters():
+            prm.copy_(prm + 0.3 * torch.randn(prm.shape, generator=gen, dtype=prm.dtype))
+
+
+def sd_arrays(module):
+    return {"sd." + k: v for k, v in module.state_dict().items()}
+
+
+def grid_reference_points(def_tr, shapes, valid_ratios):
+    return def_tr.DeformableTransformerEncoder.get_reference_points(shapes, valid_ratios, device="cpu")
+
+
+def make_module_fixtures(mods, devis_tr, def_tr):
+    torch.set_default_dtype(torch.float64)
+    gen = torch.Generator().manual_seed(77)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=gen, dtype=torch.float64)
+
+    c, heads, nl = 32, 4, 2
+    shapes = torch.as_tensor([(6, 8), (3, 4)], dtype=torch.long)
+    s = int(shapes.prod(1).sum())
+    lsi = lsi_of(shapes)
+
+    # ---- plain MSDeformAttn (A4), 2-d and 4-d reference points, padding mask
+    mod = mods.MSDeformAttn(d_model=c, n_levels=nl, n_heads=heads, n_points=3).double()
+    randomize(mod, gen)
+    n, lq = 2, 7
+    query, inp = rnd(n, lq, c), rnd(n, s, c)
+    mask = torch.rand(n, s, generator=gen) < 0.15
+    for tag, ref in (("2d", torch.rand(n, lq, nl, 2, generator=gen)),
+                     ("4d", torch.cat([torch.rand(n, lq, nl, 2, generator=gen),
+                                       0.1 + 0.4 * torch.rand(n, lq, nl, 2, generator=gen)], -1))):
+        q_ = query.clone().requires_grad_(True)
+        i_ = inp.clone().requires_grad_(True)
+        out, _ = mod(q_, ref, i_, shapes, lsi, mask)
+        gout = rnd(*out.shape)
+        gq, gi = torch.autograd.grad(out, (q_, i_), gout)
+        save(f"mod_msda_{tag}", query=query, ref=ref, inp=inp, shapes=shapes, lsi=lsi, mask=mask,
+             out=out, gout=gout, gquery=gq, ginp=gi, cfg=np.array([c, nl, heads, 3]), **sd_arrays(mod))
+
+    # ---- temporal encoder (A5+A6), all-frames mode and window mode
+    def temporal_tables(t_frames, mode, t_window):
+        enc = devis_tr.DeVISTransformerEncoder.__new__(devis_tr.DeVISTransformerEncoder)
+        torch.nn.Module.__init__(enc)
+        captured = {}
+
+        class Capture(torch.nn.Module):
+            def forward(self, output, pos, reference_points, shapes_pair, lsi_pair, temporal_offsets):
+                captured.update(ref=reference_points, shapes_pair=shapes_pair, lsi_pair=lsi_pair,
+                                temporal_offsets=temporal_offsets)
+                return output
+
+        enc.layers = torch.nn.ModuleList([Capture()])
+        enc.num_layers = 1
+        enc.t_window = t_window
+        enc.enc_connect_all_embeddings = (mode == "all")
+        valid = 0.7 + 0.3 * torch.rand(t_frames, nl, 2, generator=gen)
+        enc(rnd(t_frames, s, c), shapes, lsi, valid)
+        captured["valid_ratios"] = valid
+        return captured
+
+    for tag, t_frames, mode, t_window in (("all", 3, "all", 2), ("window", 4, "window", 2)):
+        tab = temporal_tables(t_frames, mode, t_window)
+        save(f"book_enc_{tag}", shapes=shapes, lsi=lsi, valid_ratios=tab["valid_ratios"], ref=tab["ref"],
+             tshapes=tab["shapes_pair"][1], tlsi=tab["lsi_pair"][1],
+             temporal_offsets=torch.stack(tab["temporal_offsets"]), t_window=np.array(t_window),
+             connect_all=np.array(mode == "all"))
+        mod = mods.TemporalMSDeformAttnEncoder(n_frames=t_frames, d_model=c, n_levels=nl, t_window=t_window,
+                                               n_heads=heads, n_curr_points=2, n_temporal_points=2).double()
+        randomize(mod, gen)
+        query, inp = rnd(t_frames, s, c), rnd(t_frames, s, c)
+        q_ = query.clone().requires_grad_(True)
+        i_ = inp.clone().requires_grad_(True)
+        out, _ = mod(q_, tab["ref"], i_, tab["shapes_pair"], tab["lsi_pair"], tab["temporal_offsets"])
+        gout = rnd(*out.shape)
+        grads = torch.autograd.grad(out, (q_, i_) + tuple(mod.parameters()), gout)
+        pg = {"pg." + k: g for (k, _), g in zip(mod.named_parameters(), grads[2:])}
+        save(f"mod_tenc_{tag}", query=query, ref=tab["ref"], inp=inp, shapes=shapes, lsi=lsi,
+             tshapes=tab["shapes_pair"][1], tlsi=tab["lsi_pair"][1],
+             temporal_offsets=torch.stack(tab["temporal_offsets"]), out=out, gout=gout,
+             gquery=grads[0], ginp=grads[1], cfg=np.array([t_frames, c, nl, t_window, heads, 2, 2]),
+             **sd_arrays(mod), **pg)
+
+    # ---- temporal decoder (A7): 2-d / 4-d reference points x instance-aware on / off
+    t_frames, q, t_window = 3, 5, 2
+    dec = devis_tr.DeVISTransformerDecoder.__new__(devis_tr.DeVISTransformerDecoder)
+    torch.nn.Module.__init__(dec)
+    captured = {}
+
+    class CaptureDec(torch.nn.Module):
+        def forward(self, output, query_pos, ref_in, src, shapes_pair, lsi_pair, temporal_offsets):
+            captured.update(ref_in=ref_in, shapes_pair=shapes_pair, lsi_pair=lsi_pair,
+                            temporal_offsets=temporal_offsets)
+            return output
+
+    dec.layers = torch.nn.ModuleList([CaptureDec()])
+    dec.num_layers = 1
+    dec.refine_reference_point = lambda lid, output, ref, inter, inter_ref: (ref, inter + [output], inter_ref + [ref])
+    valid = 0.7 + 0.3 * torch.rand(t_frames, nl, 2, generator=gen)
+    for tag, last in (("2d", 2), ("4d", 4)):
+        ref = torch.rand(1, t_frames * q, last, generator=gen)
+        if last == 4:
+            ref[..., 2:] = 0.1 + 0.4 * ref[..., 2:]
+        dec(rnd(1, t_frames * q, c), ref, rnd(t_frames, s, c), shapes, lsi, valid)
+        ref_in = captured["ref_in"]
+        save(f"book_dec_{tag}", shapes=shapes, lsi=lsi, valid_ratios=valid, ref=ref, ref_in=ref_in,
+             tshapes=captured["shapes_pair"][1], tlsi=captured["lsi_pair"][1],
+             temporal_offsets=torch.stack(captured["temporal_offsets"]))
+        for ia in (True, False):
+            mod = mods.TemporalMSDeformAttnDecoder(n_frames=t_frames, d_model=c, n_levels=nl, t_window=t_window,
+                                                   n_heads=heads, n_curr_points=2, n_temporal_points=2,
+                                                   dec_instance_aware_att=ia).double()
+            randomize(mod, gen)
+            query, inp = rnd(1, t_frames * q, c), rnd(t_frames, s, c)
+            q_ = query.clone().requires_grad_(True)
+            i_ = inp.clone().requires_grad_(True)
+            r_ = ref_in.clone().requires_grad_(True)
+            out, locs_c, locs_t, aw_c, aw_t = mod(q_, r_, i_, captured["shapes_pair"], captured["lsi_pair"],
+                                                  captured["temporal_offsets"])
+            gout = rnd(*out.shape)
+            gq, gi, gr = torch.autograd.grad(out, (q_, i_, r_), gout)
+            save(f"mod_tdec_{tag}_{'ia' if ia else 'noia'}", query=query, ref=ref_in, inp=inp, shapes=shapes,
+                 lsi=lsi, tshapes=captured["shapes_pair"][1], tlsi=captured["lsi_pair"][1],
+                 temporal_offsets=torch.stack(captured["temporal_offsets"]), out=out, gout=gout, gquery=gq,
+                 ginp=gi, gref=gr, loc_curr=torch.stack(locs_c), loc_temporal=torch.stack(locs_t),
+                 aw_curr=aw_c, aw_temporal=aw_t,
+                 cfg=np.array([t_frames, c, nl, t_window, heads, 2, 2, int(ia)]), **sd_arrays(mod))
+    torch.set_default_dtype(torch.float32)
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit("the reference is not mounted; fixtures can only be regenerated in the build container")
+    func_mod, mods_mod, devis_tr_mod, def_tr_mod = import_reference()
+    make_op_fixtures(func_mod)
+    make_module_fixtures(mods_mod, devis_tr_mod, def_tr_mod)
