@@ -1,0 +1,117 @@
+"""Host-side description of a clip's value pyramid for the whole-clip temporal op.
+
+The reference keeps ``spatial_shapes`` / ``level_start_index`` / ``temporal_offsets`` as device
+tensors that its kernels dereference (cuda/ms_deform_attn_cuda.cu:67-68) and rebuilds repeated
+"temporal" copies of them for every forward (devis_transformer.py:94-118,147-154).  The whole-clip
+kernels take the per-frame level table and the (T, t_window) frame table as kernel parameters
+instead, so they are needed on the host.  ``ClipGeometry`` is that host copy; ``from_reference_args``
+derives it from the reference's module arguments with one device->host read that is cached per
+tensor (all 12 attention layers of a forward share the same tensors).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+
+def all_frames_table(n_frames):
+    """devis_transformer.py:96-100,147-151: every other frame in frame order -> (T, T-1) frame indices."""
+    return [[f for f in range(n_frames) if f != t] for t in range(n_frames)]
+
+
+def window_table(n_frames, t_window):
+    """devis_transformer.py:102-112: +-t_window/2 neighbours, reflected at the clip ends (a frame can
+    then appear twice in a row of the table)."""
+    deltas = [d for d in range(-t_window // 2, t_window // 2 + 1) if d != 0]
+    return [[t + (-d if (t + d < 0 or t + d > n_frames - 1) else d) for d in deltas] for t in range(n_frames)]
+
+
+class ClipGeometry:
+    def __init__(self, shapes, n_frames, frame_table, level_start_index=None):
+        shapes = [(int(h), int(w)) for h, w in shapes]
+        self.shapes = shapes
+        self.n_levels = len(shapes)
+        self.n_frames = int(n_frames)
+        areas = [h * w for h, w in shapes]
+        if level_start_index is None:
+            level_start_index = [int(x) for x in np.concatenate([[0], np.cumsum(areas)[:-1]])]
+        self.level_start_index = [int(x) for x in level_start_index]
+        self.spatial_size = max(st + a for st, a in zip(self.level_start_index, areas))
+        table = [[int(f) for f in row] for row in frame_table] if frame_table is not None else [[] for _ in range(n_frames)]
+        if len(table) != self.n_frames or any(len(r) != len(table[0]) for r in table):
+            raise ValueError("frame_table must have one equally long row per frame")
+        if any(f < 0 or f >= self.n_frames for r in table for f in r):
+            raise ValueError("frame_table entry outside [0, n_frames)")
+        self.frame_table = table
+        self.t_window = len(table[0]) if table else 0
+        # C-ABI views (kept alive by self)
+        self._shapes_np = np.ascontiguousarray(np.array(shapes, dtype=np.int64).reshape(-1, 2))
+        self._lsi_np = np.ascontiguousarray(np.array(self.level_start_index, dtype=np.int64))
+        self._frames_np = np.ascontiguousarray(np.array(table, dtype=np.int32).reshape(self.n_frames, -1))
+        self.shapes_ptr = self._shapes_np.ctypes.data_as(ctypes.c_void_p)
+        self.lsi_ptr = self._lsi_np.ctypes.data_as(ctypes.c_void_p)
+        self.frames_ptr = self._frames_np.ctypes.data_as(ctypes.c_void_p) if self.t_window else None
+        self._orders = {}
+
+    # ------------------------------------------------------------------------------------------
+    def tile_order(self, device, tile_h=8, tile_w=8):
+        """Permutation of the S pixel-queries of one frame (encoder self-attention: query i is pixel i,
+        deformable_transformer.py:184-198) that walks every level in tile_h x tile_w tiles.  Only
+        meaningful when num_query == spatial_size and levels are stored back to back."""
+        key = (str(device), tile_h, tile_w)
+        if key not in self._orders:
+            order = []
+            for (h, w), start in zip(self.shapes, self.level_start_index):
+                idx = np.arange(h * w, dtype=np.int64).reshape(h, w) + start
+                for y0 in range(0, h, tile_h):
+                    for x0 in range(0, w, tile_w):
+                        order.append(idx[y0:y0 + tile_h, x0:x0 + tile_w].reshape(-1))
+            perm = np.concatenate(order).astype(np.int32)
+            assert np.array_equal(np.sort(perm), np.arange(self.spatial_size, dtype=np.int32)), \
+                "tile order needs back-to-back levels"
+            self._orders[key] = torch.from_numpy(perm).to(device)
+        return self._orders[key]
+
+
+# ------------------------------------------------------------------------------------------------
+_host_cache = {}
+
+
+def _host_list(t):
+    """device int tensor -> nested python list, one synchronising read per (tensor storage, version)."""
+    if not isinstance(t, torch.Tensor):
+        return [list(r) if hasattr(r, "__len__") else int(r) for r in t]
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    hit = _host_cache.get(key)
+    if hit is None:
+        if len(_host_cache) > 256:
+            _host_cache.clear()
+        hit = t.tolist()
+        _host_cache[key] = hit
+    return hit
+
+
+_geom_cache = {}
+
+
+def from_reference_args(n_frames, input_spatial_shapes, input_level_start_index, temporal_offsets):
+    """Build (and memoise) the geometry from the arguments the reference modules receive
+    (ms_deform_attn.py:268-284): the (current, temporal) shape / start-index pairs and the list of
+    per-frame temporal offset tensors."""
+    cur_shapes = input_spatial_shapes[0] if isinstance(input_spatial_shapes, (tuple, list)) else input_spatial_shapes
+    cur_lsi = input_level_start_index[0] if isinstance(input_level_start_index, (tuple, list)) else input_level_start_index
+    shapes = tuple(tuple(r) for r in _host_list(cur_shapes))
+    lsi = tuple(_host_list(cur_lsi))
+    if isinstance(temporal_offsets, torch.Tensor):
+        offs = _host_list(temporal_offsets)
+    else:
+        offs = [_host_list(o) for o in temporal_offsets]
+    table = tuple(tuple(int(o) + t for o in row) for t, row in enumerate(offs))
+    key = (n_frames, shapes, lsi, table)
+    geom = _geom_cache.get(key)
+    if geom is None:
+        if len(_geom_cache) > 64:
+            _geom_cache.clear()
+        geom = ClipGeometry(shapes, n_frames, table, lsi)
+        _geom_cache[key] = geom
+    return geom

@@ -1,0 +1,361 @@
+// msda_capi.cu -- C ABI (include/devis_msda.h) of the sm_100a multi-scale deformable attention library.
+//
+// Host side of the drop-in boundary: validates the operands the way the reference's C++ host does
+// (cuda/ms_deform_attn_cuda.cu:28-52,93-119), picks a kernel, launches on the caller's stream and
+// reports launch failures as error codes.  No torch types, no allocation, no synchronisation.
+#include <atomic>
+#include <cstring>
+
+#include "../../include/devis_msda.h"
+#include "msda_bwd.cuh"
+#include "msda_common.cuh"
+#include "msda_fwd.cuh"
+#include "msda_generic.cuh"
+
+using namespace devis;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local int t_last_cuda_error = 0;
+std::atomic<int> g_tuning[8];
+
+int cuda_fail(cudaError_t e)
+{
+    t_last_cuda_error = (int)e;
+    return DEVIS_MSDA_ERR_CUDA;
+}
+
+int check_launch()
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DEVIS_MSDA_OK : cuda_fail(e);
+}
+
+size_t elem_size(int dtype) { return dtype == DEVIS_MSDA_F64 ? 8 : dtype == DEVIS_MSDA_BF16 ? 2 : 4; }
+
+// channel counts served by the grouped-lane kernels: D = 4 * LPG
+int lanes_per_group(int dtype, int D)
+{
+    if (dtype == DEVIS_MSDA_F64) return 0;
+    return D == 32 ? 8 : D == 16 ? 4 : 0;
+}
+
+struct LaunchShape {
+    int threads, qpg;
+};
+
+LaunchShape pick_shape(int Lq, int lpg, int key_threads, int key_qpg)
+{
+    LaunchShape s;
+    s.threads = g_tuning[key_threads].load();
+    s.qpg = g_tuning[key_qpg].load();
+    if (s.threads == 0) s.threads = Lq >= 1024 ? 256 : Lq >= 128 ? 128 : 64;
+    if (s.qpg == 0) s.qpg = 1;
+    if (s.threads < 32) s.threads = 32;
+    if (s.threads > 256) s.threads = 256;
+    s.threads = (s.threads / 32) * 32;
+    if (s.qpg != 1 && s.qpg != 2 && s.qpg != 4) s.qpg = 1;
+    (void)lpg;
+    return s;
+}
+
+template <class SlotSrc>
+int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
+{
+    const OpDims &d = a.d;
+    if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
+    const size_t smem = (size_t)a.n_slots_total * sizeof(int4);
+    const int lpg = lanes_per_group(dtype, d.D);
+    if (lpg) {
+        const LaunchShape s = pick_shape(d.Lq, lpg, 0, 1);
+        const int qc = s.threads / lpg;
+        const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
+        if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+        const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
+#define DEVIS_FWD(BF, LPG, QPG) msda_fwd_kernel<BF, LPG, QPG, SlotSrc><<<grid, s.threads, smem, st>>>(a)
+#define DEVIS_FWD_Q(BF, LPG)                        \
+    do {                                            \
+        if (s.qpg == 4) DEVIS_FWD(BF, LPG, 4);      \
+        else if (s.qpg == 2) DEVIS_FWD(BF, LPG, 2); \
+        else DEVIS_FWD(BF, LPG, 1);                 \
+    } while (0)
+        if (dtype == DEVIS_MSDA_BF16) {
+            if (lpg == 8) DEVIS_FWD_Q(true, 8);
+            else DEVIS_FWD_Q(true, 4);
+        } else {
+            if (lpg == 8) DEVIS_FWD_Q(false, 8);
+            else DEVIS_FWD_Q(false, 4);
+        }
+#undef DEVIS_FWD_Q
+#undef DEVIS_FWD
+        return check_launch();
+    }
+    const int threads = 128, wpc = threads / 32;
+    const long long blocks = ((long long)d.Lq * d.M + wpc - 1) / wpc;
+    if (blocks > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    const dim3 grid((unsigned)blocks, (unsigned)d.outer);
+    if (dtype == DEVIS_MSDA_F32) msda_fwd_generic_kernel<float, SlotSrc><<<grid, threads, smem, st>>>(a);
+    else if (dtype == DEVIS_MSDA_F64) msda_fwd_generic_kernel<double, SlotSrc><<<grid, threads, smem, st>>>(a);
+    else msda_fwd_generic_kernel<__nv_bfloat16, SlotSrc><<<grid, threads, smem, st>>>(a);
+    return check_launch();
+}
+
+template <class SlotSrc>
+int launch_backward(const BwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
+{
+    const OpDims &d = a.d;
+    if (a.grad_value) {  // the reference's at::zeros_like(value), ms_deform_attn_cuda.cu:121
+        const size_t bytes = (size_t)d.outer * d.S * d.M * d.D * (dtype == DEVIS_MSDA_F64 ? 8 : 4);
+        if (bytes) {
+            const cudaError_t e = cudaMemsetAsync(a.grad_value, 0, bytes, st);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+    }
+    if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
+    const size_t smem = (size_t)a.n_slots_total * sizeof(int4);
+    const int lpg = lanes_per_group(dtype, d.D);
+    if (lpg) {
+        const LaunchShape s = pick_shape(d.Lq, lpg, 2, 3);
+        const int qc = s.threads / lpg;
+        const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
+        if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+        const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
+#define DEVIS_BWD(BF, LPG, QPG) msda_bwd_kernel<BF, LPG, QPG, SlotSrc><<<grid, s.threads, smem, st>>>(a)
+#define DEVIS_BWD_Q(BF, LPG)                        \
+    do {                                            \
+        if (s.qpg == 2) DEVIS_BWD(BF, LPG, 2);      \
+        else DEVIS_BWD(BF, LPG, 1);                 \
+    } while (0)
+        if (dtype == DEVIS_MSDA_BF16) {
+            if (lpg == 8) DEVIS_BWD_Q(true, 8);
+            else DEVIS_BWD_Q(true, 4);
+        } else {
+            if (lpg == 8) DEVIS_BWD_Q(false, 8);
+            else DEVIS_BWD_Q(false, 4);
+        }
+#undef DEVIS_BWD_Q
+#undef DEVIS_BWD
+        return check_launch();
+    }
+    const int threads = 128, wpc = threads / 32;
+    const long long blocks = ((long long)d.Lq * d.M + wpc - 1) / wpc;
+    if (blocks > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    const dim3 grid((unsigned)blocks, (unsigned)d.outer);
+    if (dtype == DEVIS_MSDA_F32) msda_bwd_generic_kernel<float, SlotSrc><<<grid, threads, smem, st>>>(a);
+    else if (dtype == DEVIS_MSDA_F64) msda_bwd_generic_kernel<double, SlotSrc><<<grid, threads, smem, st>>>(a);
+    else msda_bwd_generic_kernel<__nv_bfloat16, SlotSrc><<<grid, threads, smem, st>>>(a);
+    return check_launch();
+}
+
+int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
+{
+    if (dtype != DEVIS_MSDA_F32 && dtype != DEVIS_MSDA_F64 && dtype != DEVIS_MSDA_BF16) return DEVIS_MSDA_ERR_BAD_DTYPE;
+    if (outer < 0 || S < 0 || M <= 0 || D <= 0 || L <= 0 || Lq < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (outer > 65535) return DEVIS_MSDA_ERR_TOO_LARGE;
+    // value rows are indexed with 31 bits (bit 31 carries a flag in the grouped kernels)
+    if ((long long)outer * S >= (1LL << 31)) return DEVIS_MSDA_ERR_TOO_LARGE;
+    return DEVIS_MSDA_OK;
+}
+
+int fill_clip_table(ClipTable &tb, const int64_t *shapes, const int64_t *lsi, const int32_t *frames, int T, int S,
+                    int L, int Wt)
+{
+    if (L > kMaxLevels || (long long)T * Wt > kMaxFrameTable || T > 255) return DEVIS_MSDA_ERR_TOO_LARGE;
+    std::memset(&tb, 0, sizeof(tb));
+    tb.L = L;
+    tb.Wt = Wt;
+    for (int l = 0; l < L; ++l) {
+        const int64_t H = shapes[2 * l], W = shapes[2 * l + 1], st = lsi[l];
+        if (H <= 0 || W <= 0 || st < 0 || st + H * W > S) return DEVIS_MSDA_ERR_BAD_SHAPE;
+        tb.H[l] = (int)H;
+        tb.W[l] = (int)W;
+        tb.lsi[l] = (int)st;
+    }
+    for (int i = 0; i < T * Wt; ++i) {
+        if (frames[i] < 0 || frames[i] >= T) return DEVIS_MSDA_ERR_BAD_FRAME_TABLE;
+        tb.frame[i] = (uint8_t)frames[i];
+    }
+    return DEVIS_MSDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int devis_msda_abi_version(void) { return DEVIS_MSDA_ABI_VERSION; }
+
+const char *devis_msda_error_string(int code)
+{
+    switch (code) {
+        case DEVIS_MSDA_OK: return "ok";
+        case DEVIS_MSDA_ERR_NULL_POINTER: return "null pointer for a non-empty tensor";
+        case DEVIS_MSDA_ERR_BAD_SHAPE: return "invalid dimension";
+        case DEVIS_MSDA_ERR_BAD_DTYPE: return "unsupported dtype code";
+        case DEVIS_MSDA_ERR_BATCH_STEP: return "batch must be divisible by min(batch, im2col_step)";
+        case DEVIS_MSDA_ERR_TOO_LARGE: return "tensor too large for the kernels' indexing";
+        case DEVIS_MSDA_ERR_WORKSPACE: return "workspace missing or too small";
+        case DEVIS_MSDA_ERR_CUDA: return "CUDA runtime error (see devis_msda_last_cuda_error)";
+        case DEVIS_MSDA_ERR_UNSUPPORTED: return "no kernel for this request in this build";
+        case DEVIS_MSDA_ERR_BAD_FRAME_TABLE: return "frame table entry outside [0, num_frames)";
+        default: return "unknown error code";
+    }
+}
+
+int devis_msda_last_cuda_error(void) { return t_last_cuda_error; }
+uint64_t devis_msda_launch_count(void) { return g_launches.load(); }
+
+int devis_msda_set_tuning(int key, int value)
+{
+    if (key < 0 || key >= 8) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    g_tuning[key].store(value);
+    return DEVIS_MSDA_OK;
+}
+
+int devis_msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_loc, const void *attn_weight, void *output, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                       int num_point, int im2col_step, int dtype, void *stream)
+{
+    int rc = check_common(batch, spatial_size, num_heads, channels, num_levels, num_query, dtype);
+    if (rc) return rc;
+    if (num_point <= 0 || im2col_step <= 0 || num_levels > kMaxSlots) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (batch > 0 && batch % (batch < im2col_step ? batch : im2col_step) != 0) return DEVIS_MSDA_ERR_BATCH_STEP;
+    const bool empty = batch == 0 || num_query == 0;
+    if (!empty && (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    FwdArgs<DeviceLevels> a{};
+    a.value = value;
+    a.out = output;
+    a.seg[0] = Segment{sampling_loc, attn_weight, nullptr, nullptr, num_levels, num_point};
+    a.n_seg = 1;
+    a.n_slots_total = num_levels;
+    a.src = DeviceLevels{spatial_shapes, level_start_index};
+    a.d = OpDims{batch, spatial_size, num_heads, channels, num_query};
+    a.q_perm = nullptr;
+    return launch_forward(a, dtype, (cudaStream_t)stream);
+}
+
+size_t devis_msda_backward_workspace_bytes(int, int, int, int, int, int, int, int, unsigned) { return 0; }
+
+int devis_msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                        void *grad_value, void *grad_sampling_loc, void *grad_attn_weight, int batch,
+                        int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                        int num_point, int im2col_step, int dtype, unsigned flags, void *workspace,
+                        size_t workspace_bytes, void *stream)
+{
+    (void)workspace;
+    (void)workspace_bytes;
+    int rc = check_common(batch, spatial_size, num_heads, channels, num_levels, num_query, dtype);
+    if (rc) return rc;
+    if (num_point <= 0 || im2col_step <= 0 || num_levels > kMaxSlots) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (batch > 0 && batch % (batch < im2col_step ? batch : im2col_step) != 0) return DEVIS_MSDA_ERR_BATCH_STEP;
+    if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
+    const bool empty = batch == 0 || num_query == 0;
+    if (!empty && (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight ||
+                   !grad_output || !grad_sampling_loc || !grad_attn_weight))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    if (want_gv && !grad_value && (size_t)batch * spatial_size > 0) return DEVIS_MSDA_ERR_NULL_POINTER;
+    BwdArgs<DeviceLevels> a{};
+    a.value = value;
+    a.grad_out = grad_output;
+    a.grad_value = want_gv ? reinterpret_cast<float *>(grad_value) : nullptr;
+    a.seg[0] = Segment{sampling_loc, attn_weight, grad_sampling_loc, grad_attn_weight, num_levels, num_point};
+    a.n_seg = 1;
+    a.n_slots_total = num_levels;
+    a.src = DeviceLevels{spatial_shapes, level_start_index};
+    a.d = OpDims{batch, spatial_size, num_heads, channels, num_query};
+    a.q_perm = nullptr;
+    return launch_backward(a, dtype, (cudaStream_t)stream);
+}
+
+int devis_tmsda_forward(const void *value, const int64_t *spatial_shapes_host,
+                        const int64_t *level_start_index_host, const int32_t *frame_table_host,
+                        const void *loc_curr, const void *aw_curr, const void *loc_temporal,
+                        const void *aw_temporal, void *output, const int32_t *query_order, int num_frames,
+                        int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                        int n_curr_points, int n_temporal_points, int t_window, int dtype, void *stream)
+{
+    int rc = check_common(num_frames, spatial_size, num_heads, channels, num_levels, num_query, dtype);
+    if (rc) return rc;
+    if (n_curr_points <= 0 || n_temporal_points < 0 || t_window < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (dtype == DEVIS_MSDA_F64 && false) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const bool temporal = t_window > 0 && n_temporal_points > 0;
+    if (!spatial_shapes_host || !level_start_index_host || (temporal && !frame_table_host))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    const bool empty = num_frames == 0 || num_query == 0;
+    if (!empty && (!value || !loc_curr || !aw_curr || !output || (temporal && (!loc_temporal || !aw_temporal))))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    FwdArgs<ClipTable> a{};
+    rc = fill_clip_table(a.src, spatial_shapes_host, level_start_index_host, frame_table_host, num_frames,
+                         spatial_size, num_levels, temporal ? t_window : 0);
+    if (rc) return rc;
+    a.value = value;
+    a.out = output;
+    a.seg[0] = Segment{loc_curr, aw_curr, nullptr, nullptr, num_levels, n_curr_points};
+    a.n_seg = 1;
+    a.n_slots_total = num_levels;
+    if (temporal) {
+        a.seg[1] = Segment{loc_temporal, aw_temporal, nullptr, nullptr, t_window * num_levels, n_temporal_points};
+        a.n_seg = 2;
+        a.n_slots_total += t_window * num_levels;
+    }
+    if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
+    a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
+    a.q_perm = query_order;
+    return launch_forward(a, dtype, (cudaStream_t)stream);
+}
+
+size_t devis_tmsda_backward_workspace_bytes(int, int, int, int, int, int, int, int, int, int, unsigned) { return 0; }
+
+int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
+                         const int64_t *level_start_index_host, const int32_t *frame_table_host,
+                         const void *loc_curr, const void *aw_curr, const void *loc_temporal,
+                         const void *aw_temporal, const void *grad_output, void *grad_value,
+                         void *grad_loc_curr, void *grad_aw_curr, void *grad_loc_temporal,
+                         void *grad_aw_temporal, const int32_t *query_order, int num_frames, int spatial_size,
+                         int num_heads, int channels, int num_levels, int num_query, int n_curr_points,
+                         int n_temporal_points, int t_window, int dtype, unsigned flags, void *workspace,
+                         size_t workspace_bytes, void *stream)
+{
+    (void)workspace;
+    (void)workspace_bytes;
+    int rc = check_common(num_frames, spatial_size, num_heads, channels, num_levels, num_query, dtype);
+    if (rc) return rc;
+    if (n_curr_points <= 0 || n_temporal_points < 0 || t_window < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const bool temporal = t_window > 0 && n_temporal_points > 0;
+    if (!spatial_shapes_host || !level_start_index_host || (temporal && !frame_table_host))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
+    const bool empty = num_frames == 0 || num_query == 0;
+    if (!empty && (!value || !loc_curr || !aw_curr || !grad_output || !grad_loc_curr || !grad_aw_curr ||
+                   (temporal && (!loc_temporal || !aw_temporal || !grad_loc_temporal || !grad_aw_temporal))))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    if (want_gv && !grad_value && (size_t)num_frames * spatial_size > 0) return DEVIS_MSDA_ERR_NULL_POINTER;
+    BwdArgs<ClipTable> a{};
+    rc = fill_clip_table(a.src, spatial_shapes_host, level_start_index_host, frame_table_host, num_frames,
+                         spatial_size, num_levels, temporal ? t_window : 0);
+    if (rc) return rc;
+    a.value = value;
+    a.grad_out = grad_output;
+    a.grad_value = want_gv ? reinterpret_cast<float *>(grad_value) : nullptr;
+    a.seg[0] = Segment{loc_curr, aw_curr, grad_loc_curr, grad_aw_curr, num_levels, n_curr_points};
+    a.n_seg = 1;
+    a.n_slots_total = num_levels;
+    if (temporal) {
+        a.seg[1] = Segment{loc_temporal, aw_temporal, grad_loc_temporal, grad_aw_temporal, t_window * num_levels,
+                           n_temporal_points};
+        a.n_seg = 2;
+        a.n_slots_total += t_window * num_levels;
+    }
+    if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
+    a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
+    a.q_perm = query_order;
+    return launch_backward(a, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

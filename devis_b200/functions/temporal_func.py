@@ -1,0 +1,122 @@
+"""Whole-clip temporal multi-scale deformable attention as ONE autograd op.
+
+The reference computes a layer's temporal attention with a Python loop over the T query frames:
+per frame one ``MSDeformAttnFunction.apply`` on the frame's own value, a gather copy
+``value[temporal_frames].flatten(0, 1)``, a second ``apply`` on that copy with the temporal frames
+stacked along the level axis, and an add (modules/ms_deform_attn.py:435-460 encoder, :325-404
+decoder) -- 2T launches, T copies and 2T materialised outputs forward, the same again backward.
+``TemporalMSDeformAttnFunction`` does the whole clip in one launch each way: value (T,S,M,D) is read
+in place through the frame table, current and temporal taps accumulate into the same registers, and
+the backward scatters straight into grad_value (T,S,M,D) -- no copies, no index_add.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _lib
+from .. import MultiScaleDeformableAttention as MSDA
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.bfloat16: _lib.BF16}
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() else None
+
+
+def _aux(t, value):
+    want = torch.float32 if value.dtype == torch.bfloat16 else value.dtype
+    t = t if t.dtype == want else t.to(want)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _dims(value, loc_curr, loc_temporal, geom):
+    t, s, m, d = value.shape
+    lq = loc_curr.shape[1]
+    pc = loc_curr.shape[4]
+    pt = loc_temporal.shape[4] if loc_temporal is not None and geom.t_window else 0
+    if t != geom.n_frames or s != geom.spatial_size:
+        raise RuntimeError(f"value {tuple(value.shape)} does not match the clip geometry "
+                           f"(frames {geom.n_frames}, rows {geom.spatial_size})")
+    if loc_curr.shape[3] != geom.n_levels:
+        raise RuntimeError("loc_curr level axis does not match the clip geometry")
+    if pt and loc_temporal.shape[3] != geom.t_window * geom.n_levels:
+        raise RuntimeError("loc_temporal level axis must be t_window * n_levels")
+    return t, s, m, d, lq, pc, pt
+
+
+class TemporalMSDeformAttnFunction(Function):
+    """apply(value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry, query_order=None) -> (T, Lq, M*D)
+
+    value (T,S,M,D); loc_curr (T,Lq,M,L,Pc,2); aw_curr (T,Lq,M,L,Pc); loc_temporal (T,Lq,M,Wt*L,Pt,2);
+    aw_temporal (T,Lq,M,Wt*L,Pt) -- exactly the tensors the reference's per-frame loop slices
+    (ms_deform_attn.py:437-457); geometry is a devis_b200.clip_geometry.ClipGeometry."""
+
+    @staticmethod
+    def forward(ctx, value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry, query_order=None):
+        if not value.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")
+        if value.dtype not in _DTYPES:
+            raise RuntimeError(f'"temporal_ms_deform_attn" not implemented for \'{value.dtype}\'')
+        value = value if value.is_contiguous() else value.contiguous()
+        lc, ac = _aux(loc_curr, value), _aux(aw_curr, value)
+        has_t = geometry.t_window > 0 and loc_temporal is not None
+        lt = _aux(loc_temporal, value) if has_t else None
+        at = _aux(aw_temporal, value) if has_t else None
+        t, s, m, d, lq, pc, pt = _dims(value, lc, lt, geometry)
+        out = torch.empty((t, lq, m * d), dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.load().devis_tmsda_forward(
+                _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr,
+                _ptr(lc), _ptr(ac), _ptr(lt), _ptr(at), _ptr(out), _ptr(query_order),
+                t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0,
+                _DTYPES[value.dtype], stream))
+        ctx.geometry = geometry
+        ctx.has_t = has_t
+        ctx.in_dtypes = (loc_curr.dtype, aw_curr.dtype,
+                         loc_temporal.dtype if has_t else None, aw_temporal.dtype if has_t else None)
+        ctx.save_for_backward(value, lc, ac, lt, at, query_order)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, lc, ac, lt, at, query_order = ctx.saved_tensors
+        geometry, has_t = ctx.geometry, ctx.has_t
+        t, s, m, d, lq, pc, pt = _dims(value, lc, lt, geometry)
+        gout = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
+        gout = gout if gout.is_contiguous() else gout.contiguous()
+        acc_dtype = torch.float32 if value.dtype == torch.bfloat16 else value.dtype
+        need_gv = ctx.needs_input_grad[0]
+        gv = torch.empty(value.shape, dtype=acc_dtype, device=value.device) if need_gv else None
+        glc, gac = torch.empty_like(lc), torch.empty_like(ac)
+        glt = torch.empty_like(lt) if has_t else None
+        gat = torch.empty_like(at) if has_t else None
+        flags = (_lib.FLAG_DETERMINISTIC if MSDA._deterministic else 0) | (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE)
+        lib = _lib.load()
+        code = _DTYPES[value.dtype]
+        with torch.cuda.device(value.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            ws_bytes = lib.devis_tmsda_backward_workspace_bytes(t, s, m, d, geometry.n_levels, lq, pc, pt,
+                                                                geometry.t_window if has_t else 0, code, flags)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
+            _lib.check(lib.devis_tmsda_backward(
+                _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr,
+                _ptr(lc), _ptr(ac), _ptr(lt), _ptr(at), _ptr(gout),
+                _ptr(gv), _ptr(glc), _ptr(gac), _ptr(glt), _ptr(gat), _ptr(query_order),
+                t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0,
+                code, flags, _ptr(ws), ws_bytes, stream))
+        dl, da, dlt, dat = ctx.in_dtypes
+        if gv is not None and gv.dtype != value.dtype:
+            gv = gv.to(value.dtype)
+        glc = glc if glc.dtype == dl else glc.to(dl)
+        gac = gac if gac.dtype == da else gac.to(da)
+        if has_t:
+            glt = glt if glt.dtype == dlt else glt.to(dlt)
+            gat = gat if gat.dtype == dat else gat.to(dat)
+        return gv, glc, gac, glt, gat, None, None
+
+
+def temporal_ms_deform_attn(value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry, query_order=None):
+    return TemporalMSDeformAttnFunction.apply(value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry,
+                                              query_order)

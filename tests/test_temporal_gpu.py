@@ -1,0 +1,219 @@
+"""GPU parity of the whole-clip temporal op and of the temporal modules.
+
+ * against the golden module fixtures (outputs and gradients of the reference's own
+   TemporalMSDeformAttnEncoder / Decoder / MSDeformAttn modules, float64),
+ * against the PyTorch oracle's per-frame loop (oracle/temporal_torch.py) at a reduced clip,
+ * and, at the full DeVIS R50 T=6 shape, through size-independent properties:
+   whole-clip == the reference's 2T per-frame calls made with the drop-in op; linearity of the op in
+   value and in the attention weights; Euler identities <grad_value, value> = <grad_aw, aw> = <grad_out, out>.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, nmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(g, k, dtype=None):
+    x = torch.from_numpy(g[k]).cuda()
+    return x.to(dtype) if dtype is not None and x.is_floating_point() else x
+
+
+def _load_sd(mod, g, dtype):
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    assert set(sd) == set(mod.state_dict())            # parameter names are the reference's
+    mod.load_state_dict(sd)
+    return mod.to("cuda", dtype)
+
+
+@pytest.mark.parametrize("tag", ["2d", "4d"])
+def test_msdeformattn_module_matches_reference_module(tag):
+    from devis_b200 import MSDeformAttn
+    g = load_golden(f"mod_msda_{tag}")
+    c, nl, heads, pts = [int(x) for x in g["cfg"]]
+    for dtype, tol_o, tol_g in ((torch.float64, 1e-11, 1e-10), (torch.float32, 2e-5, 2e-4)):
+        mod = _load_sd(MSDeformAttn(c, nl, heads, pts), g, dtype)
+        q = _t(g, "query", dtype).requires_grad_(True)
+        x = _t(g, "inp", dtype).requires_grad_(True)
+        out, none = mod(q, _t(g, "ref", dtype), x, _t(g, "shapes"), _t(g, "lsi"), _t(g, "mask"))
+        assert none is None
+        out.backward(_t(g, "gout", dtype))
+        assert nmax(out.detach().cpu().numpy(), g["out"]) < tol_o
+        assert nmax(q.grad.cpu().numpy(), g["gquery"]) < tol_g
+        assert nmax(x.grad.cpu().numpy(), g["ginp"]) < tol_g
+
+
+@pytest.mark.parametrize("tag", ["all", "window"])
+def test_temporal_encoder_module_matches_reference_module(tag):
+    from devis_b200 import TemporalMSDeformAttnEncoder
+    g = load_golden(f"mod_tenc_{tag}")
+    t_frames, c, nl, t_window, heads, pc, pt = [int(x) for x in g["cfg"]]
+    for dtype, tol_o, tol_g in ((torch.float64, 1e-11, 1e-10), (torch.float32, 2e-5, 2e-4)):
+        mod = _load_sd(TemporalMSDeformAttnEncoder(t_frames, c, nl, t_window, heads, pc, pt), g, dtype)
+        q = _t(g, "query", dtype).requires_grad_(True)
+        x = _t(g, "inp", dtype).requires_grad_(True)
+        offs = [row for row in _t(g, "temporal_offsets")]
+        out, none = mod(q, _t(g, "ref", dtype), x, (_t(g, "shapes"), _t(g, "tshapes")), (_t(g, "lsi"), _t(g, "tlsi")), offs)
+        assert none is None
+        out.backward(_t(g, "gout", dtype))
+        assert nmax(out.detach().cpu().numpy(), g["out"]) < tol_o
+        assert nmax(q.grad.cpu().numpy(), g["gquery"]) < tol_g
+        assert nmax(x.grad.cpu().numpy(), g["ginp"]) < tol_g
+        for name, prm in mod.named_parameters():
+            assert nmax(prm.grad.cpu().numpy(), g["pg." + name]) < tol_g, name
+
+
+@pytest.mark.parametrize("tag", ["2d_ia", "2d_noia", "4d_ia", "4d_noia"])
+def test_temporal_decoder_module_matches_reference_module(tag):
+    from devis_b200 import TemporalMSDeformAttnDecoder
+    g = load_golden(f"mod_tdec_{tag}")
+    t_frames, c, nl, t_window, heads, pc, pt, ia = [int(x) for x in g["cfg"]]
+    for dtype, tol_o, tol_g in ((torch.float64, 1e-11, 1e-10), (torch.float32, 2e-5, 2e-4)):
+        mod = _load_sd(TemporalMSDeformAttnDecoder(t_frames, c, nl, t_window, heads, pc, pt, bool(ia)), g, dtype)
+        q = _t(g, "query", dtype).requires_grad_(True)
+        x = _t(g, "inp", dtype).requires_grad_(True)
+        r = _t(g, "ref", dtype).requires_grad_(True)
+        offs = [row for row in _t(g, "temporal_offsets")]
+        out, lc, lt, awc, awt = mod(q, r, x, (_t(g, "shapes"), _t(g, "tshapes")), (_t(g, "lsi"), _t(g, "tlsi")), offs)
+        out.backward(_t(g, "gout", dtype))
+        assert out.shape == g["out"].shape and len(lc) == t_frames and len(lt) == t_frames
+        assert tuple(lc[0].shape) == g["loc_curr"].shape[1:] and tuple(lt[0].shape) == g["loc_temporal"].shape[1:]
+        assert nmax(out.detach().cpu().numpy(), g["out"]) < tol_o
+        assert nmax(torch.stack(lc).detach().cpu().numpy(), g["loc_curr"]) < tol_o
+        assert nmax(torch.stack(lt).detach().cpu().numpy(), g["loc_temporal"]) < tol_o
+        assert nmax(awc.detach().cpu().numpy(), g["aw_curr"]) < tol_o
+        assert nmax(awt.detach().cpu().numpy(), g["aw_temporal"]) < tol_o
+        assert nmax(q.grad.cpu().numpy(), g["gquery"]) < tol_g
+        assert nmax(x.grad.cpu().numpy(), g["ginp"]) < tol_g
+        assert nmax(r.grad.cpu().numpy(), g["gref"]) < tol_g
+
+
+def _clip_fn(clip, dtype=None, order=None):
+    from devis_b200 import clip_geometry, temporal_ms_deform_attn
+    geom = clip_geometry.ClipGeometry(clip["shapes"], clip["value"].shape[0], clip["frame_table"])
+    leaves = [clip[k].clone().requires_grad_(True) for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
+    out = temporal_ms_deform_attn(*leaves, geom, order)
+    out.backward(clip["grad_out"])
+    return out.detach(), [x.grad for x in leaves], geom
+
+
+@pytest.mark.parametrize("dist", ["local", "uniform"])
+@pytest.mark.parametrize("queries", [None, 7])
+def test_whole_clip_op_matches_pytorch_oracle_per_frame_loop(dist, queries):
+    """reduced clip (T=4, 3 levels) so the CPU oracle runs in seconds; fp32 CUDA vs fp64 oracle"""
+    from devis_b200 import synthetic
+    from oracle import temporal_torch
+    shapes = ((18, 30), (9, 15), (5, 8))
+    clip = synthetic.make_clip(n_frames=4, shapes=shapes, queries=queries, dist=dist, seed=3, device="cuda")
+    out, grads, _ = _clip_fn(clip)
+    cpu = {k: (v.detach().double().cpu() if isinstance(v, torch.Tensor) else v) for k, v in clip.items()}
+    leaves = [cpu[k].clone().requires_grad_(True) for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
+    offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(clip["frame_table"])]
+    ref = temporal_torch.temporal_core_per_frame(*leaves, torch.tensor(shapes), offs)
+    ref.backward(cpu["grad_out"])
+    assert nmax(out.cpu().numpy(), ref.detach().numpy()) < 1e-5
+    for got, leaf in zip(grads, leaves):
+        assert nmax(got.cpu().numpy(), leaf.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_whole_clip_equals_reference_call_sequence_at_full_devis_shape(dtype):
+    """the reference's 2T calls + T gather copies (ms_deform_attn.py:435-460) issued with the drop-in op
+    must give what the single whole-clip launch gives -- full R50 T=6 encoder shape"""
+    from devis_b200 import MSDeformAttnFunction, synthetic
+    clip = synthetic.make_clip(dist="local", seed=1, dtype=dtype, device="cuda")
+    out, grads, geom = _clip_fn(clip)
+    order = geom.tile_order("cuda")
+    out_tiled, grads_tiled, _ = _clip_fn(clip, order=order)
+    shapes = torch.tensor(clip["shapes"], device="cuda")
+    areas = shapes.prod(1)
+    lsi = torch.cat([areas.new_zeros(1), areas.cumsum(0)[:-1]])
+    wt = len(clip["frame_table"][0])
+    tshapes = shapes.repeat(wt, 1)
+    tareas = tshapes.prod(1)
+    tlsi = torch.cat([tareas.new_zeros(1), tareas.cumsum(0)[:-1]])
+    leaves = [clip[k].clone().requires_grad_(True) for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
+    v, lc, ac, lt, at = leaves
+    frames_out = []
+    for t in range(v.shape[0]):
+        cur = MSDeformAttnFunction.apply(v[t][None], shapes, lsi, lc[t][None], ac[t][None], 64)
+        stacked = v[clip["frame_table"][t]].flatten(0, 1)[None]
+        tmp = MSDeformAttnFunction.apply(stacked, tshapes, tlsi, lt[t][None], at[t][None], 64)
+        frames_out.append(cur + tmp)
+    ref = torch.cat(frames_out, 0)
+    ref.backward(clip["grad_out"])
+    tol_o, tol_g = (2e-6, 2e-5) if dtype == torch.float32 else (1e-2, 2e-2)
+    for o, gs in ((out, grads), (out_tiled, grads_tiled)):
+        assert nmax(o.float().cpu().numpy(), ref.detach().float().cpu().numpy()) < tol_o
+        for got, leaf in zip(gs, leaves):
+            assert nmax(got.float().cpu().numpy(), leaf.grad.float().cpu().numpy()) < tol_g
+    assert torch.equal(out, out_tiled)            # the visiting order must not change any output bit
+
+
+def test_full_shape_linearity_and_euler_identities():
+    from devis_b200 import synthetic
+    clip = synthetic.make_clip(dist="local", seed=2, device="cuda")
+    out, grads, geom = _clip_fn(clip)
+    gv, glc, gac, glt, gat = grads
+    gout = clip["grad_out"]
+    total = (gout.double() * out.double()).sum().item()
+    # out is linear in value, and linear in the (current, temporal) weights jointly
+    assert abs((gv.double() * clip["value"].double()).sum().item() - total) < 1e-6 * abs(total) + 1e-3
+    aw_side = (gac.double() * clip["aw_curr"].double()).sum().item() + (gat.double() * clip["aw_temporal"].double()).sum().item()
+    assert abs(aw_side - total) < 1e-6 * abs(total) + 1e-3
+    # linearity in value: f(2.5*v + v2) = 2.5*f(v) + f(v2)
+    from devis_b200 import temporal_ms_deform_attn
+    v2 = torch.randn_like(clip["value"])
+    args = (clip["loc_curr"], clip["aw_curr"], clip["loc_temporal"], clip["aw_temporal"], geom)
+    lhs = temporal_ms_deform_attn(2.5 * clip["value"] + v2, *args)
+    rhs = 2.5 * out + temporal_ms_deform_attn(v2, *args)
+    assert nmax(lhs.cpu().numpy(), rhs.cpu().numpy()) < 1e-5
+    # a constant value map is reproduced exactly where all taps fall inside: sum of weights (=1) * const
+    const = torch.ones_like(clip["value"])
+    inside = temporal_ms_deform_attn(const, *args)
+    assert inside.max().item() <= 1 + 1e-5 and inside.min().item() >= -1e-6
+
+
+def test_decoder_shape_300_queries_whole_clip_vs_per_frame():
+    from devis_b200 import synthetic
+    from oracle import c_oracle
+    clip = synthetic.make_clip(queries=300, dist="uniform", seed=4, device="cuda")
+    out, grads, _ = _clip_fn(clip)
+    # frame 3 via the C oracle: current call + temporal call on the gathered frames
+    t = 3
+    shapes = np.array(clip["shapes"], dtype=np.int64)
+    areas = shapes.prod(1)
+    lsi = np.concatenate([[0], np.cumsum(areas)[:-1]])
+    cur = c_oracle.forward(clip["value"][t][None].cpu().numpy(), shapes, lsi, clip["loc_curr"][t][None].cpu().numpy(),
+                           clip["aw_curr"][t][None].cpu().numpy())
+    frames = clip["frame_table"][t]
+    tshapes = np.tile(shapes, (len(frames), 1))
+    tlsi = np.concatenate([[0], np.cumsum(tshapes.prod(1))[:-1]])
+    tmp = c_oracle.forward(clip["value"][frames].flatten(0, 1)[None].cpu().numpy(), tshapes, tlsi,
+                           clip["loc_temporal"][t][None].cpu().numpy(), clip["aw_temporal"][t][None].cpu().numpy())
+    assert nmax(out[t].cpu().numpy(), (cur + tmp)[0]) < 1e-5
+
+
+def test_duplicate_frames_in_table_and_no_temporal_window():
+    """window mode can list a frame twice (devis_transformer.py:102-112); t_window = 0 degenerates to the plain op"""
+    from devis_b200 import clip_geometry, synthetic, temporal_ms_deform_attn
+    from oracle import temporal_torch
+    shapes = ((10, 12), (5, 6))
+    clip = synthetic.make_clip(n_frames=4, shapes=shapes, queries=9, dist="uniform", seed=8, device="cuda", t_window=2)
+    table = clip_geometry.window_table(4, 2)
+    assert table[0] == [1, 1]
+    geom = clip_geometry.ClipGeometry(shapes, 4, table)
+    out = temporal_ms_deform_attn(clip["value"], clip["loc_curr"], clip["aw_curr"], clip["loc_temporal"],
+                                  clip["aw_temporal"], geom)
+    offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(table)]
+    cpu = lambda k: clip[k].double().cpu()
+    ref = temporal_torch.temporal_core_per_frame(cpu("value"), cpu("loc_curr"), cpu("loc_temporal"), cpu("aw_curr"),
+                                                 cpu("aw_temporal"), torch.tensor(shapes), offs)
+    assert nmax(out.cpu().numpy(), ref.numpy()) < 1e-5
+    geom0 = clip_geometry.ClipGeometry(shapes, 4, None)
+    out0 = temporal_ms_deform_attn(clip["value"], clip["loc_curr"], clip["aw_curr"], None, None, geom0)
+    from oracle import msda_torch
+    ref0 = msda_torch.msda_forward_torch(cpu("value"), torch.tensor(shapes), cpu("loc_curr"), cpu("aw_curr"))
+    assert nmax(out0.cpu().numpy(), ref0.numpy()) < 1e-5
