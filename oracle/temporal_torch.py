@@ -67,12 +67,13 @@ def temporal_projections(sd, query, input_flatten, n_heads, n_levels, t_window, 
     return value, off_c, off_t, aw_c, aw_t
 
 
-def temporal_core_per_frame(value, loc_curr, loc_temporal, aw_curr, aw_temporal, shapes,
+def temporal_core_per_frame(value, loc_curr, aw_curr, loc_temporal, aw_temporal, shapes,
                             temporal_offsets):
     """The reference's unit of work for one layer-clip: per query frame one op call on
     the frame's own value, one gather-copy of the other frames' values and one op
     call on that copy (ms_deform_attn.py:435-460).  value (T,S,M,D); loc_curr
-    (T,Lq,M,L,P,2); loc_temporal (T,Lq,M,Wt*L,P,2); returns (T,Lq,M*D)."""
+    (T,Lq,M,L,P,2); aw_curr (T,Lq,M,L,P); loc_temporal (T,Lq,M,Wt*L,P,2); aw_temporal
+    (T,Lq,M,Wt*L,P); returns (T,Lq,M*D)."""
     n_frames = value.shape[0]
     wt = temporal_offsets[0].numel()
     t_shapes = shapes.repeat(wt, 1)
@@ -130,7 +131,7 @@ def temporal_encoder_forward(sd, query, reference_points, input_flatten, shapes,
     value, off_c, off_t, aw_c, aw_t = temporal_projections(sd, query, input_flatten, n_heads,
                                                            n_levels, t_window, pc, pt)
     loc_c, loc_t = encoder_locations(reference_points, off_c, off_t, shapes, t_window)
-    core = temporal_core_per_frame(value, loc_c, loc_t, aw_c, aw_t, shapes, temporal_offsets)
+    core = temporal_core_per_frame(value, loc_c, aw_c, loc_t, aw_t, shapes, temporal_offsets)
     return F.linear(core, sd["output_proj.weight"], sd["output_proj.bias"])
 
 
@@ -148,7 +149,7 @@ def temporal_decoder_forward(sd, query, reference_points, input_flatten, shapes,
                                                            n_levels, t_window, pc, pt)
     loc_c, loc_t = decoder_locations(reference_points, off_c, off_t, shapes, t_window,
                                      temporal_offsets, pc, pt, instance_aware)
-    core = temporal_core_per_frame(value, loc_c, loc_t, aw_c, aw_t, shapes, temporal_offsets)
+    core = temporal_core_per_frame(value, loc_c, aw_c, loc_t, aw_t, shapes, temporal_offsets)
     out = F.linear(core.flatten(0, 1)[None], sd["output_proj.weight"], sd["output_proj.bias"])
     return (out, [loc_c[t][None] for t in range(n_frames)],
             [loc_t[t][None] for t in range(n_frames)], aw_c, aw_t)

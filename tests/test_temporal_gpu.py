@@ -24,6 +24,7 @@ def _t(g, k, dtype=None):
 def _load_sd(mod, g, dtype):
     sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
     assert set(sd) == set(mod.state_dict())            # parameter names are the reference's
+    mod = mod.double()                                  # fixtures are float64: load before any down-cast
     mod.load_state_dict(sd)
     return mod.to("cuda", dtype)
 
@@ -209,7 +210,7 @@ def test_duplicate_frames_in_table_and_no_temporal_window():
                                   clip["aw_temporal"], geom)
     offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(table)]
     cpu = lambda k: clip[k].double().cpu()
-    ref = temporal_torch.temporal_core_per_frame(cpu("value"), cpu("loc_curr"), cpu("loc_temporal"), cpu("aw_curr"),
+    ref = temporal_torch.temporal_core_per_frame(cpu("value"), cpu("loc_curr"), cpu("aw_curr"), cpu("loc_temporal"),
                                                  cpu("aw_temporal"), torch.tensor(shapes), offs)
     assert nmax(out.cpu().numpy(), ref.numpy()) < 1e-5
     geom0 = clip_geometry.ClipGeometry(shapes, 4, None)
