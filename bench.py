@@ -1,0 +1,342 @@
+"""bench.py -- the contract benchmark of the temporal MSDeformAttn hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp32|bf16] [--dist local|uniform]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One STEP = one encoder-layer temporal attention over one clip, forward + backward, at the DeVIS R50 T=6
+YouTube-VIS shape (BASELINE.json configs[1]; SURVEY.md section 8d "unit U"): T=6 frames, levels
+(45,80),(23,40),(12,20),(6,10) -> S=4820 rows per frame, 8 heads x 32 channels, one query per pixel,
+4 current + 5x4x4 temporal points -> 96 taps per (query, head).  It is what the reference does with 12
+MSDeformAttnFunction calls + 6 gather copies of value (modules/ms_deform_attn.py:435-460) and what this
+repository does with one forward launch and one backward launch.
+
+Rank 0 prints ONE JSON line.  `value` is whole-job layer-clips per second with inputs resident in HBM;
+`e2e` is the same unit of work driven through the public autograd API from pinned HOST buffers, every
+step paying the host->device copy of its inputs and the device->host copy of its results.
+Multi-GPU: clips are independent, so each rank works on its own clip (weak scaling, no collective on
+the op path -- SURVEY.md section 8e).
+
+`--impl reference` times the reference's CPU implementation of the same unit of work (the oracle's
+PyTorch restatement of ms_deform_attn_core_pytorch + autograd, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "temporal_msda_fwd_bwd_layer_clips_per_sec"
+UNIT = "layer-clips/s"
+WORKLOAD = "DeVIS R50 T=6 encoder layer-clip: S=4820, M=8, D=32, Lq=4820/frame, K=96 taps, fwd+bwd"
+T_FRAMES, S_ROWS, HEADS, CH, K_TAPS = 6, 4820, 8, 32, 96
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), through NVML
+    (the same counters nvidia-smi prints) every 5 ms from a helper thread."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80))
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.err = f"nvml unavailable: {exc}"
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception as exc:  # noqa: BLE001
+                self.err = str(exc)
+                return
+            time.sleep(0.005)
+
+    def stop(self):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.sm), "reasons": sorted(self.reasons),
+               "power_w_max": max(self.power) if self.power else None}
+        if self.err:
+            out["note"] = self.err
+        return out
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """per-launch DRAM traffic of the dominant kernel from the committed ncu --set full capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as fh:
+            return json.load(fh)[kernel_key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_sample(reps, dist, seed=0):
+    """Times the reference's CPU path (oracle PyTorch restatement: grid_sample forward + autograd backward)
+    on ONE of the T=6 query frames of the workload: its current-frame call, the gather copy of the 5
+    other frames' value and the temporal call (2 of the 12 op calls of a layer-clip).  Returns
+    (seconds per sample [median], cores, description)."""
+    import torch
+    from devis_b200 import synthetic
+    from oracle import msda_torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    clip = synthetic.make_clip(dist=dist, seed=seed, device="cpu")
+    shapes = torch.tensor(clip["shapes"])
+    t = T_FRAMES // 2
+    frames = clip["frame_table"][t]
+    tshapes = shapes.repeat(len(frames), 1)
+    times = []
+    for _ in range(reps):
+        v = clip["value"].clone().requires_grad_(True)
+        lc, ac = clip["loc_curr"][t][None].clone().requires_grad_(True), clip["aw_curr"][t][None].clone().requires_grad_(True)
+        lt, at = clip["loc_temporal"][t][None].clone().requires_grad_(True), clip["aw_temporal"][t][None].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        cur = msda_torch.msda_forward_torch(v[t][None], shapes, lc, ac)
+        stacked = v[frames].flatten(0, 1)[None]
+        tmp = msda_torch.msda_forward_torch(stacked, tshapes, lt, at)
+        (cur + tmp).backward(clip["grad_out"][t][None])
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times), cores, "1 of 6 query frames (current call + gather copy + temporal call), fwd+autograd bwd, fp32"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    t_wall = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(1, args.dist)
+    sec, cores, sample = cpu_reference_sample(max(1, min(args.steps, 5)), args.dist)
+    per_clip = sec * T_FRAMES
+    value = 1.0 / per_clip
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_clip * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "dist": args.dist, "note": "CPU path; value extrapolated x6 from the sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist_mod
+    from devis_b200 import _lib, clip_geometry, synthetic, temporal_ms_deform_attn
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist_mod.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+    clip = synthetic.make_clip(dist=args.dist, dtype=dtype, seed=100 + rank, device=dev)
+    geom = clip_geometry.ClipGeometry(clip["shapes"], T_FRAMES, clip["frame_table"])
+    order = geom.tile_order(dev, 8, 8)
+    names = ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")
+    leaves = [clip[k].requires_grad_(True) for k in names]
+    gout = clip["grad_out"]
+
+    def step():
+        for x in leaves:
+            x.grad = None
+        out = temporal_ms_deform_attn(*leaves, geom, order)
+        out.backward(gout)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist_mod.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist_mod.all_reduce(lt, op=dist_mod.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = world / (ms_step * 1e-3)
+
+    # ---- per-kernel durations (events around each launch, same stream, same inputs) for the roofline
+    from benchmarks.sweep import RawClip
+    raw = RawClip({k: (v.detach() if hasattr(v, "detach") else v) for k, v in clip.items()}, order)
+    f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    b_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for _ in range(3):
+        raw.fwd(); raw.bwd()
+    torch.cuda.synchronize()
+    for (fa, fb), (ba, bb) in zip(f_ev, b_ev):
+        fa.record(); raw.fwd(); fb.record()
+        ba.record(); raw.bwd(); bb.record()
+    torch.cuda.synchronize()
+    us_fwd = statistics.mean(a.elapsed_time(b) for a, b in f_ev) * 1e3
+    us_bwd = statistics.mean(a.elapsed_time(b) for a, b in b_ev) * 1e3
+    elem = clip["value"].element_size()
+    bytes_f, bytes_b = synthetic.algorithmic_bytes(T_FRAMES, S_ROWS, HEADS, CH, S_ROWS, K_TAPS, elem=elem)
+    peak, peak_src = measured_peak_gbs()
+
+    # ---- e2e: public autograd API from pinned host buffers, H2D of the inputs and D2H of the results every step
+    host_in = [x.detach().cpu().pin_memory() for x in leaves] + [gout.cpu().pin_memory()]
+    dev_in = [torch.empty_like(x.detach()) for x in leaves] + [torch.empty_like(gout)]
+    host_out = None
+
+    def e2e_step():
+        nonlocal host_out
+        for h, d in zip(host_in, dev_in):
+            d.copy_(h, non_blocking=True)
+        ins = [d.requires_grad_(True) for d in dev_in[:5]]
+        out = temporal_ms_deform_attn(*ins, geom, order)
+        out.backward(dev_in[5])
+        results = [out.detach()] + [x.grad for x in ins]
+        if host_out is None:
+            host_out = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in results]
+        for h, r in zip(host_out, results):
+            h.copy_(r, non_blocking=True)
+        for d in dev_in[:5]:
+            d.requires_grad_(False)
+            d.grad = None
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(h.numel() * h.element_size() for h in host_in)
+    d2h = sum(h.numel() * h.element_size() for h in host_out)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "dist": args.dist, "taps": "boundary-safe",
+                       "l2_policy": "inputs larger than L2 (326 MB of operands per step vs 126 MB L2); no flush",
+                       "clips_per_rank_per_step": 1, "parallelism": f"clip-sharded x{world}, no collective"},
+            "us_fwd": us_fwd, "us_bwd": us_bwd,
+            "roofline": {"bound": "hbm", "kernel": "msda_bwd_kernel", "achieved": bytes_b / us_bwd / 1e3, "peak": peak,
+                         "unit": "GB/s", "frac": bytes_b / us_bwd / 1e3 / peak, "traffic": ncu_traffic("msda_bwd_kernel"),
+                         "algorithmic_bytes": bytes_b, "peak_source": peak_src,
+                         "fwd": {"kernel": "msda_fwd_kernel", "achieved": bytes_f / us_fwd / 1e3,
+                                 "frac": bytes_f / us_fwd / 1e3 / peak, "algorithmic_bytes": bytes_f,
+                                 "traffic": ncu_traffic("msda_fwd_kernel")},
+                         "fwd_bwd": {"achieved": (bytes_f + bytes_b) / (us_fwd + us_bwd) / 1e3,
+                                     "frac": (bytes_f + bytes_b) / (us_fwd + us_bwd) / 1e3 / peak},
+                         "note": "gather op: binding resource is the SM L1/shared data pipe (128 B/clk/SM), see DESIGN.md"},
+            "e2e": {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sec, cores, sample = cpu_reference_sample(2, args.dist)
+            line["cpu_baseline"] = {"value": 1.0 / (sec * T_FRAMES), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": sample + f"; {sec:.2f} s per sample, x6 per layer-clip"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist_mod.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--dist", default="local", choices=["local", "uniform"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,8 +18,9 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--tile", default="8x8")
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--qpg", type=int, default=0)
+ap.add_argument("--sigma", type=float, default=2.0)
 a = ap.parse_args()
-clip = synthetic.make_clip(dist=a.dist, dtype={"fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype], device="cuda")
+clip = synthetic.make_clip(dist=a.dist, dtype={"fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype], device="cuda", sigma_px=a.sigma)
 geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
 order = None if a.tile == "none" else geom.tile_order("cuda", *[int(x) for x in a.tile.split("x")])
 rc = RawClip(clip, order)

@@ -72,24 +72,26 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--sigma", type=float, default=2.0)
+    ap.add_argument("--quick", action="store_true")
     a = ap.parse_args()
     dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype]
-    clip = synthetic.make_clip(dist=a.dist, dtype=dtype, queries=a.queries or None, device="cuda")
+    clip = synthetic.make_clip(dist=a.dist, dtype=dtype, queries=a.queries or None, device="cuda", sigma_px=a.sigma)
     fb, bb = synthetic.algorithmic_bytes(6, 4820, 8, 32, clip["loc_curr"].shape[1], 96, elem=clip["value"].element_size())
     rows = []
     geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
     orders = {"none": None}
     if not a.queries:
-        for th, tw in ((4, 8), (8, 8), (8, 16), (16, 16)):
+        for th, tw in (((8, 8),) if a.quick else ((4, 8), (8, 8), (8, 16), (16, 16))):
             orders[f"{th}x{tw}"] = geom.tile_order("cuda", th, tw)
     for oname, order in orders.items():
         rc = RawClip(clip, order)
-        for threads, qpg in itertools.product((128, 256), (1, 2, 4)):
+        for threads, qpg in (((256, 1), (256, 2)) if a.quick else itertools.product((128, 256), (1, 2, 4))):
             _lib.set_tuning(0, threads); _lib.set_tuning(1, qpg)
             f = time_us(rc.fwd, a.iters)
             rows.append(dict(kind="fwd", order=oname, threads=threads, qpg=qpg, us=round(f, 1), gbs=round(fb / f / 1e3, 1)))
             print(rows[-1], flush=True)
-        for threads, qpg in itertools.product((128, 256), (1, 2)):
+        for threads, qpg in (((128, 1), (256, 1)) if a.quick else itertools.product((128, 256), (1, 2))):
             _lib.set_tuning(2, threads); _lib.set_tuning(3, qpg)
             b = time_us(rc.bwd, a.iters)
             rows.append(dict(kind="bwd", order=oname, threads=threads, qpg=qpg, us=round(b, 1), gbs=round(bb / b / 1e3, 1)))

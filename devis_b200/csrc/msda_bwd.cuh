@@ -7,7 +7,7 @@
 // 4 scalar atomics per (tap, channel).
 //
 // Here (same work split as msda_fwd.cuh: LPG lanes x 4 channels per (query, head), tap geometry
-// prepared by one lane per tap and broadcast by shuffles):
+// prepared by one lane per tap and handed over through the shared-memory TapExchange):
 //   * per tap each lane forms the 4 corner dot products  A_c = sum_ch grad_out[ch] * value_c[ch]
 //     over its own 4 channels only (16 FMA); everything else about grad_attn / grad_loc is linear in
 //     those four numbers, so it is done AFTER the channel reduction, once per tap, by the lane that
@@ -68,12 +68,15 @@ __device__ __forceinline__ void reduce_scatter_taps(float (&d)[LPG][4], int j, f
 template <bool BF16, int LPG, int QPG, class SlotSrc>
 __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
 {
+    using X = TapExchange<LPG>;
     extern __shared__ int4 s_slot[];
     const int outer = blockIdx.y;
     build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * X::kWordsPerWarpBuf);
 
     const int M = a.d.M, Lq = a.d.Lq;
     const int j = threadIdx.x % LPG;
+    const int g = (threadIdx.x & 31) / LPG;
     const int grp = threadIdx.x / LPG;
     const int QC = blockDim.x / LPG;
     const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
@@ -94,12 +97,17 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
         }
     }
 
-    const unsigned ps = (unsigned)(M * LPG);
-    const float4 *vb32 = reinterpret_cast<const float4 *>(a.value) + m * LPG + j;
-    const uint2 *vb16 = reinterpret_cast<const uint2 *>(a.value) + m * LPG + j;
-    float *gvb = a.grad_value ? a.grad_value + 4 * (m * LPG + j) : nullptr;
+    constexpr unsigned kQuadBytes = BF16 ? 8u : 16u;
+    const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
+    // keep the per-lane base as ONE 64-bit register pair: each corner address is then base + u32 offset
+    // (IADD3 + IADD3.X) instead of a re-derived IMAD.WIDE chain (5 instructions per address in round 1a)
+    asm volatile("" : "+l"(vbase));
+    // grad_value is always fp32: 16 bytes per channel quad; offsets published for `value` scale by 16/kQuadBytes
+    char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * 16u : nullptr;
+    constexpr unsigned kGvShift = BF16 ? 1u : 0u;
 
-    int slot_base = 0;
+    int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;
         const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
@@ -120,60 +128,57 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
                     xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
                     w = __ldg(aw + row * K + k);
                 }
-                const TapGeom g = tap_geometry(xy.x, xy.y, sl, live);
-                const float b00 = g.hh * g.hw, b01 = g.hh * g.lw, b10 = g.lh * g.hw, b11 = g.lh * g.lw;
-                const float w00 = (g.ok & 1u) ? w * b00 : 0.f;
-                const float w01 = (g.ok & 2u) ? w * b01 : 0.f;
-                const float w10 = (g.ok & 4u) ? w * b10 : 0.f;
-                const float w11 = (g.ok & 8u) ? w * b11 : 0.f;
-                const unsigned rT = (unsigned)g.rowT | ((unsigned)g.dcol << 31);
-                const unsigned rB = (unsigned)g.rowB;
+                const TapGeom t = tap_geometry(xy.x, xy.y, sl, live);
+                float *buf = xbuf + parity * X::kWordsPerWarpBuf;
+                parity ^= 1;
+                X::publish(buf, j, g, t, w, rowbytes);
+                __syncwarp();
 
+                const float4 gg = go[i];
                 float dsum[LPG][4];
 #pragma unroll
                 for (int jj = 0; jj < LPG; ++jj) {
-                    const unsigned t = __shfl_sync(0xffffffffu, rT, jj, LPG);
-                    const unsigned b = __shfl_sync(0xffffffffu, rB, jj, LPG);
-                    const float c00 = __shfl_sync(0xffffffffu, w00, jj, LPG);
-                    const float c01 = __shfl_sync(0xffffffffu, w01, jj, LPG);
-                    const float c10 = __shfl_sync(0xffffffffu, w10, jj, LPG);
-                    const float c11 = __shfl_sync(0xffffffffu, w11, jj, LPG);
-                    const unsigned dc = (t >> 31) ? ps : 0u;
-                    const size_t oT = (size_t)(t & 0x7fffffffu) * ps, oB = (size_t)b * ps;
+                    uint4 off;
+                    float4 c;
+                    X::fetch(buf, jj, g, off, c);
                     float4 v00, v01, v10, v11;
                     if (BF16) {
-                        v00 = ldg_bf16x4(vb16 + oT);
-                        v01 = ldg_bf16x4(vb16 + oT + dc);
-                        v10 = ldg_bf16x4(vb16 + oB);
-                        v11 = ldg_bf16x4(vb16 + oB + dc);
+                        v00 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.x));
+                        v01 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.y));
+                        v10 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.z));
+                        v11 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.w));
                     } else {
-                        v00 = ldg_f4(vb32 + oT);
-                        v01 = ldg_f4(vb32 + oT + dc);
-                        v10 = ldg_f4(vb32 + oB);
-                        v11 = ldg_f4(vb32 + oB + dc);
+                        v00 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.x));
+                        v01 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.y));
+                        v10 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.z));
+                        v11 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.w));
                     }
-                    const float4 gg = go[i];
-                    dsum[jj][0] = v00.x * gg.x + v00.y * gg.y + v00.z * gg.z + v00.w * gg.w;
-                    dsum[jj][1] = v01.x * gg.x + v01.y * gg.y + v01.z * gg.z + v01.w * gg.w;
-                    dsum[jj][2] = v10.x * gg.x + v10.y * gg.y + v10.z * gg.z + v10.w * gg.w;
-                    dsum[jj][3] = v11.x * gg.x + v11.y * gg.y + v11.z * gg.z + v11.w * gg.w;
+                    dsum[jj][0] = fmaf(v00.w, gg.w, fmaf(v00.z, gg.z, fmaf(v00.y, gg.y, v00.x * gg.x)));
+                    dsum[jj][1] = fmaf(v01.w, gg.w, fmaf(v01.z, gg.z, fmaf(v01.y, gg.y, v01.x * gg.x)));
+                    dsum[jj][2] = fmaf(v10.w, gg.w, fmaf(v10.z, gg.z, fmaf(v10.y, gg.y, v10.x * gg.x)));
+                    dsum[jj][3] = fmaf(v11.w, gg.w, fmaf(v11.z, gg.z, fmaf(v11.y, gg.y, v11.x * gg.x)));
                     if (gvb) {
-                        if (c00 != 0.f) red_add_f4(gvb + 4 * oT, c00 * gg.x, c00 * gg.y, c00 * gg.z, c00 * gg.w);
-                        if (c01 != 0.f) red_add_f4(gvb + 4 * (oT + dc), c01 * gg.x, c01 * gg.y, c01 * gg.z, c01 * gg.w);
-                        if (c10 != 0.f) red_add_f4(gvb + 4 * oB, c10 * gg.x, c10 * gg.y, c10 * gg.z, c10 * gg.w);
-                        if (c11 != 0.f) red_add_f4(gvb + 4 * (oB + dc), c11 * gg.x, c11 * gg.y, c11 * gg.z, c11 * gg.w);
+                        if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                        if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                        if (c.z != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.z << kGvShift)), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                        if (c.w != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.w << kGvShift)), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
                     }
                 }
 
                 float A[4];
                 reduce_scatter_taps<LPG>(dsum, j, A);
                 if (live) {
-                    const float a00 = (g.ok & 1u) ? A[0] : 0.f, a01 = (g.ok & 2u) ? A[1] : 0.f;
-                    const float a10 = (g.ok & 4u) ? A[2] : 0.f, a11 = (g.ok & 8u) ? A[3] : 0.f;
-                    const float gx = g.hh * (a01 - a00) + g.lh * (a11 - a10);
-                    const float gy = g.hw * (a10 - a00) + g.lw * (a11 - a01);
-                    const bool hit = g.ok != 0u;  // out-of-range taps write the reference's zero fill
-                    gaw[row * K + k] = hit ? b00 * a00 + b01 * a01 + b10 * a10 + b11 * a11 : 0.f;
+                    const bool hit = t.ok != 0u;  // out-of-range taps write the reference's zero fill
+                    const float hh = (t.ok & 1u) ? t.hh : 0.f, lh = (t.ok & 2u) ? t.lh : 0.f;
+                    const float hw = (t.ok & 4u) ? t.hw : 0.f, lw = (t.ok & 8u) ? t.lw : 0.f;
+                    // masked bilinear factors make every term of an outside corner vanish (its A is garbage
+                    // from the clamped row): d/dx = sum_rows rowfac * (right*[r_ok] - left*[l_ok]) etc.
+                    const float l_in = (t.ok & 4u) ? 1.f : 0.f, r_in = (t.ok & 8u) ? 1.f : 0.f;
+                    const float t_in = (t.ok & 1u) ? 1.f : 0.f, b_in = (t.ok & 2u) ? 1.f : 0.f;
+                    const float val = hh * (hw * A[0] + lw * A[1]) + lh * (hw * A[2] + lw * A[3]);
+                    const float gx = hh * (r_in * A[1] - l_in * A[0]) + lh * (r_in * A[3] - l_in * A[2]);
+                    const float gy = hw * (b_in * A[2] - t_in * A[0]) + lw * (b_in * A[3] - t_in * A[1]);
+                    gaw[row * K + k] = hit ? val : 0.f;
                     reinterpret_cast<float2 *>(gloc + row * K * 2)[k] =
                         hit ? make_float2((float)sl.y * gx * w, (float)sl.x * gy * w) : make_float2(0.f, 0.f);
                 }

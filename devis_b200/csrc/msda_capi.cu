@@ -35,11 +35,19 @@ int check_launch()
 
 size_t elem_size(int dtype) { return dtype == DEVIS_MSDA_F64 ? 8 : dtype == DEVIS_MSDA_BF16 ? 2 : 4; }
 
-// channel counts served by the grouped-lane kernels: D = 4 * LPG
-int lanes_per_group(int dtype, int D)
+// channel counts served by the grouped-lane kernels: D = 4 * LPG.  They address value with 32-bit byte
+// offsets, so tensors of 4 GiB and more go to the generic kernels.
+int lanes_per_group(int dtype, const OpDims &d)
 {
     if (dtype == DEVIS_MSDA_F64) return 0;
-    return D == 32 ? 8 : D == 16 ? 4 : 0;
+    const unsigned long long bytes = (unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype);
+    if (bytes >= (1ull << 32)) return 0;
+    return d.D == 32 ? 8 : d.D == 16 ? 4 : 0;
+}
+
+size_t exchange_bytes(int lpg, int threads)
+{
+    return (size_t)(threads / 32) * (lpg == 8 ? TapExchange<8>::kBytesPerWarp : TapExchange<4>::kBytesPerWarp);
 }
 
 struct LaunchShape {
@@ -66,10 +74,11 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
 {
     const OpDims &d = a.d;
     if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
-    const size_t smem = (size_t)a.n_slots_total * sizeof(int4);
-    const int lpg = lanes_per_group(dtype, d.D);
+    size_t smem = (size_t)a.n_slots_total * sizeof(int4);
+    const int lpg = lanes_per_group(dtype, d);
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, lpg, 0, 1);
+        smem += exchange_bytes(lpg, s.threads);
         const int qc = s.threads / lpg;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
         if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
@@ -114,10 +123,11 @@ int launch_backward(const BwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
         }
     }
     if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
-    const size_t smem = (size_t)a.n_slots_total * sizeof(int4);
-    const int lpg = lanes_per_group(dtype, d.D);
+    size_t smem = (size_t)a.n_slots_total * sizeof(int4);
+    const int lpg = lanes_per_group(dtype, d);
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, lpg, 2, 3);
+        smem += exchange_bytes(lpg, s.threads);
         const int qc = s.threads / lpg;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
         if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;

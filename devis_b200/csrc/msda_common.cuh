@@ -85,16 +85,20 @@ __device__ __forceinline__ void build_slots(int4 *s_slot, const ClipTable &tb, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// One tap's geometry, computed by ONE lane and then shared with the lanes that own the channels.
+// One tap's geometry, computed by ONE lane and then handed to the lanes that own the channels.
 // Mirrors cuda/ms_deform_im2col_cuda.cuh:281-288 (pixel coordinate and range test) and :38-52,80
-// (floor cell, bilinear weights); rounding sequence of the coordinate is the reference's:
-// round(round(loc*size) - 0.5), no FMA contraction.
+// (floor cell, bilinear weights); the rounding sequence of the coordinate is the reference's:
+// round(round(loc*size) - 0.5), no FMA contraction, so floor() picks the reference's cell.
+//
+// Corners outside the map get a ZERO weight factor and a clamped (always in-bounds) row, so the
+// consumer does four unconditional 16-byte loads per tap with no predicates: the reference's
+// "if (h_low >= 0 && w_low >= 0) ..." guards (cuh:56-78) become multiplications by zero.
 // ---------------------------------------------------------------------------------------------
 struct TapGeom {
-    float lh, lw, hh, hw;  // fractional parts and their complements
-    int rowT, rowB;        // clamped value rows of the top-left / bottom-left corner
-    int dcol;              // 0 or 1: clamped column step to the right corners
-    unsigned ok;           // bit0 TL, bit1 TR, bit2 BL, bit3 BR corner inside the map; 0 if tap out of range
+    float lh, lw, hh, hw;    // fractional parts and complements (unmasked; the backward needs them)
+    int rTL, rTR, rBL, rBR;  // clamped value rows of the 4 corners
+    unsigned ok;             // bit0 top row, bit1 bottom row, bit2 left column, bit3 right column inside the
+                             // map; 0 if the whole tap fails the reference's range test
 };
 
 __device__ __forceinline__ TapGeom tap_geometry(float x, float y, const int4 slot, bool live)
@@ -110,14 +114,70 @@ __device__ __forceinline__ TapGeom tap_geometry(float x, float y, const int4 slo
     g.lw = w_im - wf;
     g.hh = 1.f - g.lh;
     g.hw = 1.f - g.lw;
-    const bool t_ok = h0 >= 0, b_ok = h0 + 1 <= H - 1, l_ok = w0 >= 0, r_ok = w0 + 1 <= W - 1;
-    g.ok = inb ? ((t_ok && l_ok) | ((t_ok && r_ok) << 1) | ((b_ok && l_ok) << 2) | ((b_ok && r_ok) << 3)) : 0u;
+    g.ok = inb ? ((unsigned)(h0 >= 0) | ((unsigned)(h0 + 1 <= H - 1) << 1) | ((unsigned)(w0 >= 0) << 2) |
+                  ((unsigned)(w0 + 1 <= W - 1) << 3))
+               : 0u;
     const int h0c = max(h0, 0), h1c = min(h0 + 1, H - 1), w0c = max(w0, 0), w1c = min(w0 + 1, W - 1);
-    g.rowT = slot.z + h0c * W + w0c;
-    g.rowB = slot.z + h1c * W + w0c;
-    g.dcol = w1c - w0c;
+    const int top = slot.z + h0c * W, bot = slot.z + h1c * W;
+    g.rTL = top + w0c;
+    g.rTR = top + w1c;
+    g.rBL = bot + w0c;
+    g.rBR = bot + w1c;
     return g;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tap exchange through shared memory.  A group of LPG lanes owns one (query, head); lane j prepares
+// tap k0+j and publishes a 32-byte record; then all lanes of the group walk the LPG records.
+// (Round-1 profile: doing this with __shfl_sync cost 6 L1-data-pipe wavefronts per tap -- shuffles
+// are counted in l1tex__data_pipe_lsu_wavefronts_mem_shared -- against 16 for the four corner
+// gathers; two broadcast LDS.128 cost 2.)
+//   record = { u32 byte offset of TL, TR, BL, BR corner rows | w*hh, w*lh, hw, lw }   (masked factors)
+// Layout per warp and buffer: [tap j][group slot], slot = g ^ (j & 3): readers (fixed j, 4 groups)
+// and writers (fixed g, 8 taps; halves written in swapped order for j >= 4) are bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+template <int LPG>
+struct TapExchange {
+    static constexpr int GPW = 32 / LPG;                 // groups per warp
+    static constexpr int kWordsPerWarpBuf = LPG * GPW * 8;
+    static constexpr int kBytesPerWarp = 2 * kWordsPerWarpBuf * 4;  // double buffered
+
+    __device__ static __forceinline__ int rec_word(int j, int g) { return (j * GPW + (g ^ (j & (GPW - 1)))) * 8; }
+
+    __device__ static __forceinline__ void publish(float *buf, int j, int g, const TapGeom &t, float w, unsigned rowbytes)
+    {
+        const bool live = t.ok != 0u;
+        uint4 off;
+        off.x = (unsigned)t.rTL * rowbytes;
+        off.y = (unsigned)t.rTR * rowbytes;
+        off.z = (unsigned)t.rBL * rowbytes;
+        off.w = (unsigned)t.rBR * rowbytes;
+        float4 f;
+        f.x = (live && (t.ok & 1u)) ? w * t.hh : 0.f;
+        f.y = (live && (t.ok & 2u)) ? w * t.lh : 0.f;
+        f.z = (t.ok & 4u) ? t.hw : 0.f;
+        f.w = (t.ok & 8u) ? t.lw : 0.f;
+        float *r = buf + rec_word(j, g);
+        if (j & 4) {
+            *reinterpret_cast<float4 *>(r + 4) = f;
+            *reinterpret_cast<uint4 *>(r) = off;
+        } else {
+            *reinterpret_cast<uint4 *>(r) = off;
+            *reinterpret_cast<float4 *>(r + 4) = f;
+        }
+    }
+
+    __device__ static __forceinline__ void fetch(const float *buf, int jj, int g, uint4 &off, float4 &c)
+    {
+        const float *r = buf + rec_word(jj, g);
+        off = *reinterpret_cast<const uint4 *>(r);
+        const float4 f = *reinterpret_cast<const float4 *>(r + 4);
+        c.x = f.x * f.z;  // TL
+        c.y = f.x * f.w;  // TR
+        c.z = f.y * f.z;  // BL
+        c.w = f.y * f.w;  // BR
+    }
+};
 
 // 16-byte read-only loads / vector reductions --------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float4 *p) { return __ldg(p); }

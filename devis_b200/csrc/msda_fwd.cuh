@@ -8,8 +8,9 @@
 //     (128 B for D=32 fp32): 4 corner loads per tap are 4 fully used L1 wavefronts per warp;
 //   * tap geometry is computed ONCE per tap: lane j of the group reads location / weight of tap
 //     k0+j (coalesced over the group), does the floor / range test / bilinear weights with the
-//     attention weight folded in, and the group then walks the LPG taps broadcasting the 6 words
-//     (2 row indices, 4 weights) with width-LPG shuffles;
+//     attention weight folded in, and publishes a 32-byte record (4 byte offsets, 4 weight factors)
+//     in a per-warp shared-memory exchange; the group then walks the LPG records with two broadcast
+//     LDS.128 each (TapExchange in msda_common.cuh; shuffles were measured to cost 3x the L1 wavefronts);
 //   * a CTA works on ONE head and QC*QPG queries, and walks slots in order, so that its working set
 //     at any time is one (frame, level, head) neighbourhood of value -- the L1/L2 locality that the
 //     whole-clip op relies on; QPG queries per group are interleaved (accumulators in registers).
@@ -36,14 +37,17 @@ struct FwdArgs {
 template <bool BF16, int LPG, int QPG, class SlotSrc>
 __global__ void __launch_bounds__(256) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
 {
+    using X = TapExchange<LPG>;
     extern __shared__ int4 s_slot[];
     const int outer = blockIdx.y;
     build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * X::kWordsPerWarpBuf);
 
     const int M = a.d.M, Lq = a.d.Lq;
-    const int j = threadIdx.x % LPG;          // channel-quad owned by this lane == tap it prepares
-    const int grp = threadIdx.x / LPG;
-    const int QC = blockDim.x / LPG;          // groups (queries in flight) per CTA
+    const int j = threadIdx.x % LPG;          // channel quad owned by this lane == tap it prepares
+    const int g = (threadIdx.x & 31) / LPG;   // group within the warp
+    const int grp = threadIdx.x / LPG;        // group within the CTA
+    const int QC = blockDim.x / LPG;          // (query, head) pairs in flight per CTA
     const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
 
     int q[QPG];
@@ -55,16 +59,19 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
         q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
     }
 
-    // value viewed as 16-byte (fp32) / 8-byte (bf16) channel quads: row stride M*LPG quads
-    const unsigned ps = (unsigned)(M * LPG);
-    const float4 *vb32 = reinterpret_cast<const float4 *>(a.value) + m * LPG + j;
-    const uint2 *vb16 = reinterpret_cast<const uint2 *>(a.value) + m * LPG + j;
+    // value row = M*LPG channel quads; this lane reads quad (m*LPG + j) of every row it touches
+    constexpr unsigned kQuadBytes = BF16 ? 8u : 16u;
+    const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
+    // keep the per-lane base as ONE 64-bit register pair: each corner address is then base + u32 offset
+    // (IADD3 + IADD3.X) instead of a re-derived IMAD.WIDE chain (5 instructions per address in round 1a)
+    asm volatile("" : "+l"(vbase));
 
     float4 acc[QPG];
 #pragma unroll
     for (int i = 0; i < QPG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    int slot_base = 0;
+    int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;
         const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
@@ -83,39 +90,32 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
                     xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
                     w = __ldg(aw + row * K + k);
                 }
-                const TapGeom g = tap_geometry(xy.x, xy.y, sl, live);
-                const float w00 = (g.ok & 1u) ? w * g.hh * g.hw : 0.f;
-                const float w01 = (g.ok & 2u) ? w * g.hh * g.lw : 0.f;
-                const float w10 = (g.ok & 4u) ? w * g.lh * g.hw : 0.f;
-                const float w11 = (g.ok & 8u) ? w * g.lh * g.lw : 0.f;
-                const unsigned rT = (unsigned)g.rowT | ((unsigned)g.dcol << 31);
-                const unsigned rB = (unsigned)g.rowB;
+                const TapGeom t = tap_geometry(xy.x, xy.y, sl, live);
+                float *buf = xbuf + parity * X::kWordsPerWarpBuf;
+                parity ^= 1;
+                X::publish(buf, j, g, t, w, rowbytes);
+                __syncwarp();
 #pragma unroll
                 for (int jj = 0; jj < LPG; ++jj) {
-                    const unsigned t = __shfl_sync(0xffffffffu, rT, jj, LPG);
-                    const unsigned b = __shfl_sync(0xffffffffu, rB, jj, LPG);
-                    const float c00 = __shfl_sync(0xffffffffu, w00, jj, LPG);
-                    const float c01 = __shfl_sync(0xffffffffu, w01, jj, LPG);
-                    const float c10 = __shfl_sync(0xffffffffu, w10, jj, LPG);
-                    const float c11 = __shfl_sync(0xffffffffu, w11, jj, LPG);
-                    const unsigned dc = (t >> 31) ? ps : 0u;
-                    const size_t oT = (size_t)(t & 0x7fffffffu) * ps, oB = (size_t)b * ps;
+                    uint4 off;
+                    float4 c;
+                    X::fetch(buf, jj, g, off, c);
                     float4 v00, v01, v10, v11;
                     if (BF16) {
-                        v00 = ldg_bf16x4(vb16 + oT);
-                        v01 = ldg_bf16x4(vb16 + oT + dc);
-                        v10 = ldg_bf16x4(vb16 + oB);
-                        v11 = ldg_bf16x4(vb16 + oB + dc);
+                        v00 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.x));
+                        v01 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.y));
+                        v10 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.z));
+                        v11 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.w));
                     } else {
-                        v00 = ldg_f4(vb32 + oT);
-                        v01 = ldg_f4(vb32 + oT + dc);
-                        v10 = ldg_f4(vb32 + oB);
-                        v11 = ldg_f4(vb32 + oB + dc);
+                        v00 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.x));
+                        v01 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.y));
+                        v10 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.z));
+                        v11 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.w));
                     }
-                    acc[i].x += c00 * v00.x + c01 * v01.x + c10 * v10.x + c11 * v11.x;
-                    acc[i].y += c00 * v00.y + c01 * v01.y + c10 * v10.y + c11 * v11.y;
-                    acc[i].z += c00 * v00.z + c01 * v01.z + c10 * v10.z + c11 * v11.z;
-                    acc[i].w += c00 * v00.w + c01 * v01.w + c10 * v10.w + c11 * v11.w;
+                    acc[i].x = fmaf(c.w, v11.x, fmaf(c.z, v10.x, fmaf(c.y, v01.x, fmaf(c.x, v00.x, acc[i].x))));
+                    acc[i].y = fmaf(c.w, v11.y, fmaf(c.z, v10.y, fmaf(c.y, v01.y, fmaf(c.x, v00.y, acc[i].y))));
+                    acc[i].z = fmaf(c.w, v11.z, fmaf(c.z, v10.z, fmaf(c.y, v01.z, fmaf(c.x, v00.z, acc[i].z))));
+                    acc[i].w = fmaf(c.w, v11.w, fmaf(c.z, v10.w, fmaf(c.y, v01.w, fmaf(c.x, v00.w, acc[i].w))));
                 }
             }
         }
