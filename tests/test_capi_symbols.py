@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: libdevis_msda.so loads without a GPU, exports every function that
+include/devis_msda.h declares, and the Python binding types exactly those.  No compute calls."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "devis_msda.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(devis_t?msda_\w+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from devis_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_functions()
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in devis_msda.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "python binding and header disagree on the function list"
+
+
+def test_abi_version_and_error_strings_without_gpu():
+    from devis_b200 import _lib
+    lib = _lib.load()
+    assert lib.devis_msda_abi_version() == _lib.ABI_VERSION
+    header = open(HEADER).read()
+    assert f"#define DEVIS_MSDA_ABI_VERSION {_lib.ABI_VERSION}" in header
+    codes = {name: int(val) for name, val in re.findall(r"#define (DEVIS_MSDA_ERR_\w+) \((-\d+)\)", header)}
+    assert len(codes) == 9
+    for name, code in codes.items():
+        msg = lib.devis_msda_error_string(code).decode()
+        assert msg and "unknown" not in msg, name
+    assert "unknown" in lib.devis_msda_error_string(-99).decode()
+    for flag, val in (("DEVIS_MSDA_F32", _lib.F32), ("DEVIS_MSDA_F64", _lib.F64), ("DEVIS_MSDA_BF16", _lib.BF16)):
+        assert re.search(rf"#define {flag} {val}\b", header)
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    """bad dtype / shape / batch-step are rejected on the host (no device needed)"""
+    from devis_b200 import _lib
+    lib = _lib.load()
+    null = None
+    assert lib.devis_msda_forward(null, null, null, null, null, null, 1, 4, 2, 32, 1, 1, 1, 64, 7, null) == -3
+    assert lib.devis_msda_forward(null, null, null, null, null, null, 1, 4, 0, 32, 1, 1, 1, 64, 0, null) == -2
+    assert lib.devis_msda_forward(null, null, null, null, null, null, 3, 4, 2, 32, 1, 1, 1, 2, 0, null) == -4
+    assert lib.devis_msda_forward(null, null, null, null, null, null, 1, 4, 2, 32, 1, 1, 1, 64, 0, null) == -1
+    assert lib.devis_msda_backward(null, null, null, null, null, null, null, null, null, 1, 4, 2, 32, 1, 1, 1, 64, 0,
+                                   0, null, 0, null) == -1
+    # empty problems are fine with null pointers and launch nothing
+    before = lib.devis_msda_launch_count()
+    assert lib.devis_msda_forward(null, null, null, null, null, null, 0, 4, 2, 32, 1, 0, 1, 64, 0, null) == 0
+    assert lib.devis_msda_launch_count() == before
+    assert lib.devis_msda_set_tuning(99, 1) == -2 and lib.devis_msda_set_tuning(0, 0) == 0
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "devis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src.replace("(/root/reference/", "("), f

@@ -1,0 +1,119 @@
+"""CPU tests of the host-side mirror: frame tables and temporal level tables against what the reference's
+DeVISTransformerEncoder/Decoder build (golden book_* fixtures), query tile orders, module parameter layout and
+initial values, the projection stage against the oracle port, and the no-CPU-fallback contract."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from devis_b200 import clip_geometry, synthetic
+from devis_b200.modules import MSDeformAttn, TemporalMSDeformAttnDecoder, TemporalMSDeformAttnEncoder
+
+
+def test_frame_tables_match_reference_transformer_bookkeeping():
+    g = load_golden("book_enc_all")
+    t = g["temporal_offsets"].shape[0]
+    assert clip_geometry.all_frames_table(t) == (g["temporal_offsets"] + np.arange(t)[:, None]).tolist()
+    g = load_golden("book_enc_window")
+    t = g["temporal_offsets"].shape[0]
+    assert clip_geometry.window_table(t, int(g["t_window"])) == (g["temporal_offsets"] + np.arange(t)[:, None]).tolist()
+    g = load_golden("book_dec_2d")
+    assert clip_geometry.all_frames_table(3) == (g["temporal_offsets"] + np.arange(3)[:, None]).tolist()
+
+
+def test_geometry_from_reference_arguments():
+    g = load_golden("book_enc_window")
+    offs = [torch.from_numpy(r) for r in g["temporal_offsets"]]
+    geom = clip_geometry.from_reference_args(4, (torch.from_numpy(g["shapes"]), torch.from_numpy(g["tshapes"])),
+                                             (torch.from_numpy(g["lsi"]), torch.from_numpy(g["tlsi"])), offs)
+    assert geom.shapes == [tuple(r) for r in g["shapes"].tolist()]
+    assert geom.level_start_index == g["lsi"].tolist()
+    assert geom.spatial_size == int(g["shapes"].prod(1).sum()) and geom.t_window == 2
+    assert geom.frame_table[0] == [1, 1]                 # reflection lists a frame twice (devis_transformer.py:102-112)
+    # the temporal tables the reference rebuilds per forward are implied by (shapes, t_window)
+    assert np.array_equal(np.tile(g["shapes"], (geom.t_window, 1)), g["tshapes"])
+    again = clip_geometry.from_reference_args(4, (torch.from_numpy(g["shapes"]), None), (torch.from_numpy(g["lsi"]), None), offs)
+    assert again is geom                                  # memoised
+    with pytest.raises(ValueError):
+        clip_geometry.ClipGeometry([(2, 2)], 2, [[5], [0]])
+
+
+def test_tile_order_is_a_permutation_that_keeps_levels_apart():
+    geom = clip_geometry.ClipGeometry(synthetic.DEVIS_SHAPES, 6, clip_geometry.all_frames_table(6))
+    assert geom.spatial_size == 4820 and geom.level_start_index == [0, 3600, 4520, 4760]
+    for th, tw in ((8, 8), (4, 8), (16, 16)):
+        order = geom.tile_order("cpu", th, tw).numpy()
+        assert np.array_equal(np.sort(order), np.arange(4820))
+        assert order[:3600].max() < 3600 and order[3600:4520].min() >= 3600
+    first = geom.tile_order("cpu", 8, 8).numpy()[:64]
+    ys, xs = first // 80, first % 80
+    assert ys.max() == 7 and xs.max() == 7               # first 64 queries are the top-left 8x8 pixel tile of level 0
+
+
+def test_modules_have_reference_parameter_names_shapes_and_initial_values():
+    for cls, fixture, kw in ((MSDeformAttn, "mod_msda_2d", dict(d_model=32, n_levels=2, n_heads=4, n_points=3)),
+                             (TemporalMSDeformAttnEncoder, "mod_tenc_all",
+                              dict(n_frames=3, d_model=32, n_levels=2, t_window=2, n_heads=4, n_curr_points=2, n_temporal_points=2)),
+                             (TemporalMSDeformAttnDecoder, "mod_tdec_2d_ia",
+                              dict(n_frames=3, d_model=32, n_levels=2, t_window=2, n_heads=4, n_curr_points=2, n_temporal_points=2))):
+        g = load_golden(fixture)
+        mod = cls(**kw)
+        ref = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+        assert set(mod.state_dict()) == set(ref)
+        for k, v in mod.state_dict().items():
+            assert tuple(v.shape) == ref[k].shape, k
+    # initial pattern (ms_deform_attn.py:184-221): zero offset weights, head rays (i+1) steps long, zero logits
+    enc = TemporalMSDeformAttnEncoder(n_frames=6, d_model=256, n_levels=4, t_window=5, n_heads=8, n_curr_points=4,
+                                      n_temporal_points=4)
+    assert not enc.sampling_offsets.weight.any() and not enc.temporal_sampling_offsets.weight.any()
+    assert not enc.attention_weights.bias.any() and not enc.temporal_attention_weights.weight.any()
+    b = enc.sampling_offsets.bias.view(8, 4, 4, 2)
+    assert torch.allclose(b[0, :, :, 0], torch.arange(1., 5.).expand(4, 4)) and not b[0, :, :, 1].abs().max() > 1e-6
+    assert torch.allclose(b[2, 1, 3], torch.tensor([0., 4.]), atol=1e-6)
+    bt = enc.temporal_sampling_offsets.bias.view(8, 20, 4, 2)
+    assert torch.allclose(bt[:, 0], b[:, 0]) and torch.allclose(bt[:, 19], b[:, 0])
+    assert enc.im2col_step == 64 and MSDeformAttn().im2col_step == 64
+    with pytest.raises(ValueError):
+        MSDeformAttn(d_model=30, n_heads=4)
+
+
+def test_projection_stage_matches_oracle_port():
+    """_compute_deformable_attention is pure PyTorch (cuBLAS/ATen on GPU): check it on CPU against the oracle port,
+    which is pinned to the reference module by tests/test_oracle_golden.py"""
+    from oracle import temporal_torch
+    g = load_golden("mod_tenc_all")
+    t_frames, c, nl, t_window, heads, pc, pt = [int(x) for x in g["cfg"]]
+    mod = TemporalMSDeformAttnEncoder(t_frames, c, nl, t_window, heads, pc, pt).double()
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    mod.load_state_dict(sd)
+    q, x = torch.from_numpy(g["query"]), torch.from_numpy(g["inp"])
+    got = mod._compute_deformable_attention(q, x)
+    want = temporal_torch.temporal_projections(sd, q, x, heads, nl, t_window, pc, pt)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.allclose(a, b, rtol=0, atol=1e-13)
+
+
+def test_no_cpu_fallback():
+    from devis_b200 import MSDeformAttnFunction, clip_geometry as cg, temporal_ms_deform_attn
+    g = load_golden("op_d32")
+    args = [torch.from_numpy(g[k]) for k in ("value", "shapes", "lsi", "loc", "aw")]
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDeformAttnFunction.apply(*args, 64)
+    clip = synthetic.make_clip(n_frames=2, shapes=((4, 4),), heads=2, channels=32, queries=3, device="cpu")
+    geom = cg.ClipGeometry(((4, 4),), 2, clip["frame_table"])
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        temporal_ms_deform_attn(clip["value"], clip["loc_curr"], clip["aw_curr"], clip["loc_temporal"],
+                                clip["aw_temporal"], geom)
+
+
+def test_synthetic_workload_is_boundary_safe_and_sized_like_the_survey():
+    clip = synthetic.make_clip(n_frames=2, shapes=((9, 16), (5, 8)), heads=2, channels=4, device="cpu", seed=3)
+    for key, sizes in (("loc_curr", [(16, 9), (8, 5)]), ("loc_temporal", [(16, 9), (8, 5)])):
+        loc = clip[key]
+        for lvl in range(loc.shape[3]):
+            w, h = sizes[lvl % 2]
+            pix = loc[:, :, :, lvl] * torch.tensor([w, h]) - 0.5
+            frac = pix - torch.floor(pix)
+            assert frac.min() > 0.015 and frac.max() < 0.985
+    fwd, bwd = synthetic.algorithmic_bytes(6, 4820, 8, 32, 4820, 96)
+    assert (fwd, bwd) == (325754880, 621895680)          # 325.75 MB / 621.90 MB
