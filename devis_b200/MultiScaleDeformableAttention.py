@@ -19,9 +19,15 @@ _deterministic = False
 
 def set_deterministic(flag):
     """Select the bit-reproducible grad_value accumulation (the reference's float atomicAdd scatter is
-    run-to-run non-deterministic)."""
+    run-to-run non-deterministic).  Also switched on by
+    torch.use_deterministic_algorithms(True)."""
     global _deterministic
     _deterministic = bool(flag)
+
+
+def deterministic_enabled(value_dtype=None):
+    on = _deterministic or torch.are_deterministic_algorithms_enabled()
+    return on and value_dtype != torch.float64      # fp64 keeps native double atomics (gradcheck path)
 
 
 def _check(named, like=None):
@@ -100,7 +106,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty(value.shape, dtype=acc_dtype, device=value.device)
     grad_loc = torch.empty_like(loc)
     grad_aw = torch.empty_like(aw)
-    flags = _lib.FLAG_DETERMINISTIC if _deterministic else 0
+    flags = _lib.FLAG_DETERMINISTIC if deterministic_enabled(value.dtype) else 0
     lib = _lib.load()
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream

@@ -35,6 +35,7 @@ struct BwdArgs {
     const void *value;
     const void *grad_out;
     float *grad_value;  // fp32 accumulation target (also for bf16 value); nullptr = skip
+    DetScale det;       // deterministic mode: det.acc != nullptr replaces the float reductions
     Segment seg[2];
     int n_seg;
     int n_slots_total;
@@ -106,6 +107,9 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
     // grad_value is always fp32: 16 bytes per channel quad; offsets published for `value` scale by 16/kQuadBytes
     char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * 16u : nullptr;
     constexpr unsigned kGvShift = BF16 ? 1u : 0u;
+    // deterministic mode: 8-byte fixed-point accumulators, same row layout -> offsets scale by 2 * 16 / kQuadBytes
+    char *detb = a.det.acc ? reinterpret_cast<char *>(a.det.acc) + (size_t)(m * LPG + j) * 32u : nullptr;
+    const float det_sh = a.det.acc ? ldexpf(1.f, kDetFracBits - det_exponent(a.det.max_bits)) : 0.f;
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
@@ -157,7 +161,12 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
                     dsum[jj][1] = fmaf(v01.w, gg.w, fmaf(v01.z, gg.z, fmaf(v01.y, gg.y, v01.x * gg.x)));
                     dsum[jj][2] = fmaf(v10.w, gg.w, fmaf(v10.z, gg.z, fmaf(v10.y, gg.y, v10.x * gg.x)));
                     dsum[jj][3] = fmaf(v11.w, gg.w, fmaf(v11.z, gg.z, fmaf(v11.y, gg.y, v11.x * gg.x)));
-                    if (gvb) {
+                    if (detb) {
+                        if (c.x != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.x << (kGvShift + 1))), det_sh, c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                        if (c.y != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.y << (kGvShift + 1))), det_sh, c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                        if (c.z != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.z << (kGvShift + 1))), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                        if (c.w != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.w << (kGvShift + 1))), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                    } else if (gvb) {
                         if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
                         if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
                         if (c.z != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.z << kGvShift)), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);

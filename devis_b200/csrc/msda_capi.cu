@@ -111,10 +111,45 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     return check_launch();
 }
 
+// deterministic-mode workspace: [int64 accumulators: outer*S*M*D][2 x u32 max slots, padded to 16 B]
+size_t det_workspace_bytes(long long outer, long long S, long long M, long long D)
+{
+    return (size_t)(outer * S * M * D) * sizeof(long long) + 16;
+}
+
 template <class SlotSrc>
-int launch_backward(const BwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
+int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
+                    cudaStream_t st)
 {
     const OpDims &d = a.d;
+    const bool det = (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) && a.grad_value != nullptr;
+    const size_t n_value = (size_t)d.outer * d.S * d.M * d.D;
+    float *final_grad_value = a.grad_value;
+    if (det) {
+        if (dtype == DEVIS_MSDA_F64) return DEVIS_MSDA_ERR_UNSUPPORTED;
+        const size_t need = det_workspace_bytes(d.outer, d.S, d.M, d.D);
+        if (!workspace || workspace_bytes < need) return DEVIS_MSDA_ERR_WORKSPACE;
+        cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+        if (e != cudaSuccess) return cuda_fail(e);
+        a.det.acc = reinterpret_cast<long long *>(workspace);
+        unsigned *slots = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(workspace) + n_value * sizeof(long long));
+        a.det.max_bits = slots;
+        if (d.outer > 0 && d.Lq > 0) {
+            const size_t n_go = (size_t)d.outer * d.Lq * d.M * d.D;
+            const int blocks = 148 * 8;
+            if (dtype == DEVIS_MSDA_BF16) absmax_kernel<true><<<blocks, 256, 0, st>>>(a.grad_out, n_go, slots);
+            else absmax_kernel<false><<<blocks, 256, 0, st>>>(a.grad_out, n_go, slots);
+            int rc = check_launch();
+            if (rc) return rc;
+            for (int sg = 0; sg < a.n_seg; ++sg) {
+                const size_t n_aw = (size_t)d.outer * d.Lq * d.M * a.seg[sg].n_slots * a.seg[sg].P;
+                absmax_kernel<false><<<blocks, 256, 0, st>>>(a.seg[sg].aw, n_aw, slots + 1);
+                rc = check_launch();
+                if (rc) return rc;
+            }
+        }
+        a.grad_value = nullptr;  // the float reductions are replaced by the fixed-point ones
+    }
     if (a.grad_value) {  // the reference's at::zeros_like(value), ms_deform_attn_cuda.cu:121
         const size_t bytes = (size_t)d.outer * d.S * d.M * d.D * (dtype == DEVIS_MSDA_F64 ? 8 : 4);
         if (bytes) {
@@ -122,7 +157,12 @@ int launch_backward(const BwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
             if (e != cudaSuccess) return cuda_fail(e);
         }
     }
-    if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
+    auto finalize = [&]() -> int {
+        if (!det || n_value == 0) return DEVIS_MSDA_OK;
+        det_finalize_kernel<<<148 * 8, 256, 0, st>>>(a.det.acc, final_grad_value, n_value, a.det.max_bits);
+        return check_launch();
+    };
+    if (d.outer == 0 || d.Lq == 0) return finalize();
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
     const int lpg = lanes_per_group(dtype, d);
     if (lpg) {
@@ -147,7 +187,8 @@ int launch_backward(const BwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
         }
 #undef DEVIS_BWD_Q
 #undef DEVIS_BWD
-        return check_launch();
+        const int rc = check_launch();
+        return rc ? rc : finalize();
     }
     const int threads = 128, wpc = threads / 32;
     const long long blocks = ((long long)d.Lq * d.M + wpc - 1) / wpc;
@@ -156,7 +197,8 @@ int launch_backward(const BwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     if (dtype == DEVIS_MSDA_F32) msda_bwd_generic_kernel<float, SlotSrc><<<grid, threads, smem, st>>>(a);
     else if (dtype == DEVIS_MSDA_F64) msda_bwd_generic_kernel<double, SlotSrc><<<grid, threads, smem, st>>>(a);
     else msda_bwd_generic_kernel<__nv_bfloat16, SlotSrc><<<grid, threads, smem, st>>>(a);
-    return check_launch();
+    const int rc = check_launch();
+    return rc ? rc : finalize();
 }
 
 int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
@@ -247,7 +289,13 @@ int devis_msda_forward(const void *value, const int64_t *spatial_shapes, const i
     return launch_forward(a, dtype, (cudaStream_t)stream);
 }
 
-size_t devis_msda_backward_workspace_bytes(int, int, int, int, int, int, int, int, unsigned) { return 0; }
+size_t devis_msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels, int, int, int,
+                                           int dtype, unsigned flags)
+{
+    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC) || (flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE) || dtype == DEVIS_MSDA_F64)
+        return 0;
+    return det_workspace_bytes(batch, spatial_size, num_heads, channels);
+}
 
 int devis_msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                         const void *sampling_loc, const void *attn_weight, const void *grad_output,
@@ -256,13 +304,10 @@ int devis_msda_backward(const void *value, const int64_t *spatial_shapes, const 
                         int num_point, int im2col_step, int dtype, unsigned flags, void *workspace,
                         size_t workspace_bytes, void *stream)
 {
-    (void)workspace;
-    (void)workspace_bytes;
     int rc = check_common(batch, spatial_size, num_heads, channels, num_levels, num_query, dtype);
     if (rc) return rc;
     if (num_point <= 0 || im2col_step <= 0 || num_levels > kMaxSlots) return DEVIS_MSDA_ERR_BAD_SHAPE;
     if (batch > 0 && batch % (batch < im2col_step ? batch : im2col_step) != 0) return DEVIS_MSDA_ERR_BATCH_STEP;
-    if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
     const bool empty = batch == 0 || num_query == 0;
     if (!empty && (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight ||
@@ -279,7 +324,7 @@ int devis_msda_backward(const void *value, const int64_t *spatial_shapes, const 
     a.src = DeviceLevels{spatial_shapes, level_start_index};
     a.d = OpDims{batch, spatial_size, num_heads, channels, num_query};
     a.q_perm = nullptr;
-    return launch_backward(a, dtype, (cudaStream_t)stream);
+    return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int devis_tmsda_forward(const void *value, const int64_t *spatial_shapes_host,
@@ -319,7 +364,13 @@ int devis_tmsda_forward(const void *value, const int64_t *spatial_shapes_host,
     return launch_forward(a, dtype, (cudaStream_t)stream);
 }
 
-size_t devis_tmsda_backward_workspace_bytes(int, int, int, int, int, int, int, int, int, int, unsigned) { return 0; }
+size_t devis_tmsda_backward_workspace_bytes(int num_frames, int spatial_size, int num_heads, int channels, int, int,
+                                            int, int, int, int dtype, unsigned flags)
+{
+    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC) || (flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE) || dtype == DEVIS_MSDA_F64)
+        return 0;
+    return det_workspace_bytes(num_frames, spatial_size, num_heads, channels);
+}
 
 int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
                          const int64_t *level_start_index_host, const int32_t *frame_table_host,
@@ -331,12 +382,9 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
                          int n_temporal_points, int t_window, int dtype, unsigned flags, void *workspace,
                          size_t workspace_bytes, void *stream)
 {
-    (void)workspace;
-    (void)workspace_bytes;
     int rc = check_common(num_frames, spatial_size, num_heads, channels, num_levels, num_query, dtype);
     if (rc) return rc;
     if (n_curr_points <= 0 || n_temporal_points < 0 || t_window < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
-    if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool temporal = t_window > 0 && n_temporal_points > 0;
     if (!spatial_shapes_host || !level_start_index_host || (temporal && !frame_table_host))
         return DEVIS_MSDA_ERR_NULL_POINTER;
@@ -365,7 +413,7 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
     a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
     a.q_perm = query_order;
-    return launch_backward(a, dtype, (cudaStream_t)stream);
+    return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

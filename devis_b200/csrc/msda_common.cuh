@@ -198,6 +198,63 @@ __device__ __forceinline__ void red_add_f4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Deterministic grad_value (DEVIS_MSDA_FLAG_DETERMINISTIC).  Floating-point atomics make the
+// reference's grad_value run-to-run different.  Here every contribution
+// (a float product) is converted EXACTLY to a 64-bit fixed-point integer and accumulated with integer
+// reductions, which are associative: the sum does not depend on arrival order.  Scale: 2^(36 - e) with
+// 2^e > max|grad_out| * max|attn| >= every contribution (weights are <= 1), so |q| < 2^36 and 2^27
+// contributions per element fit in int64; resolution is 2^-36 of the largest possible contribution
+// (fp32 accumulation has 2^-24 of the running sum).  A finalize pass converts back to float.
+// ---------------------------------------------------------------------------------------------
+struct DetScale {
+    const unsigned *max_bits;  // [0] = bits of max|grad_out|, [1] = bits of max|attn weight| (non-negative floats)
+    long long *acc;            // (outer, S, M, D) fixed-point accumulators, zero-filled
+};
+
+constexpr int kDetFracBits = 36;
+
+__device__ __forceinline__ int det_exponent(const unsigned *max_bits)
+{
+    const float bound = __uint_as_float(max_bits[0]) * __uint_as_float(max_bits[1]);
+    int e = 0;
+    if (bound > 0.f && bound < 3.0e38f) (void)frexpf(bound, &e);   // bound = f * 2^e, f in [0.5, 1)
+    return e + 1;
+}
+
+__device__ __forceinline__ void det_add4(long long *p, float sh, float a, float b, float c, float d)
+{
+    // sh is a power of two: the products below are exact; llrint of a float is exact as well
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 0, (unsigned long long)__float2ll_rn(a * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 1, (unsigned long long)__float2ll_rn(b * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 2, (unsigned long long)__float2ll_rn(c * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 3, (unsigned long long)__float2ll_rn(d * sh));
+}
+
+// max|x| over n elements (float or bf16) into *slot, as the bits of a non-negative float (atomicMax on the
+// bit pattern is exact and order independent)
+template <bool BF16>
+__global__ void __launch_bounds__(256) absmax_kernel(const void *x, size_t n, unsigned *slot)
+{
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(x)[i])
+                             : reinterpret_cast<const float *>(x)[i];
+        m = fmaxf(m, fabsf(v));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256) det_finalize_kernel(const long long *acc, float *out, size_t n,
+                                                           const unsigned *max_bits)
+{
+    const double back = ldexp(1.0, det_exponent(max_bits) - kDetFracBits);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)((double)acc[i] * back);
+}
+
 __device__ __forceinline__ uint2 pack_bf16x4(float4 v)
 {
     const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);

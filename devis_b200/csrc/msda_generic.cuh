@@ -131,6 +131,12 @@ __global__ void __launch_bounds__(128) msda_bwd_generic_kernel(const BwdArgs<Slo
     const size_t row = ((size_t)outer * Lq + q) * M + m;
     const size_t ps = (size_t)M * D;
     C *gv = reinterpret_cast<C *>(a.grad_value);  // float for fp32/bf16, double for fp64
+    long long *det = a.det.acc;                    // deterministic fixed-point accumulators (never with fp64)
+    const float det_sh = det ? ldexpf(1.f, kDetFracBits - det_exponent(a.det.max_bits)) : 0.f;
+    auto scatter = [&](long long r, C v) {
+        if (det) atomicAdd(reinterpret_cast<unsigned long long *>(det) + r, (unsigned long long)__float2ll_rn((float)v * det_sh));
+        else if (gv) atomicAdd(gv + r, v);
+    };
 
     for (int c0 = 0; c0 < D; c0 += 32) {
         const int c = c0 + lane;
@@ -156,25 +162,25 @@ __global__ void __launch_bounds__(128) msda_bwd_generic_kernel(const BwdArgs<Slo
                         v00 = Scalar<T>::load(a.value, g.r00 * ps + ch);
                         gh -= g.hw * v00;
                         gw -= g.hh * v00;
-                        if (gv) atomicAdd(gv + g.r00 * ps + ch, g.hh * g.hw * tv);
+                        scatter(g.r00 * ps + ch, g.hh * g.hw * tv);
                     }
                     if (g.ok & 2u) {
                         v01 = Scalar<T>::load(a.value, g.r01 * ps + ch);
                         gh -= g.lw * v01;
                         gw += g.hh * v01;
-                        if (gv) atomicAdd(gv + g.r01 * ps + ch, g.hh * g.lw * tv);
+                        scatter(g.r01 * ps + ch, g.hh * g.lw * tv);
                     }
                     if (g.ok & 4u) {
                         v10 = Scalar<T>::load(a.value, g.r10 * ps + ch);
                         gh += g.hw * v10;
                         gw -= g.lh * v10;
-                        if (gv) atomicAdd(gv + g.r10 * ps + ch, g.lh * g.hw * tv);
+                        scatter(g.r10 * ps + ch, g.lh * g.hw * tv);
                     }
                     if (g.ok & 8u) {
                         v11 = Scalar<T>::load(a.value, g.r11 * ps + ch);
                         gh += g.lw * v11;
                         gw += g.lh * v11;
-                        if (gv) atomicAdd(gv + g.r11 * ps + ch, g.lh * g.lw * tv);
+                        scatter(g.r11 * ps + ch, g.lh * g.lw * tv);
                     }
                     const C val = g.hh * g.hw * v00 + g.hh * g.lw * v01 + g.lh * g.hw * v10 + g.lh * g.lw * v11;
                     p_a = top * val;

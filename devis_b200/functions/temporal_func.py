@@ -92,7 +92,7 @@ class TemporalMSDeformAttnFunction(Function):
         glc, gac = torch.empty_like(lc), torch.empty_like(ac)
         glt = torch.empty_like(lt) if has_t else None
         gat = torch.empty_like(at) if has_t else None
-        flags = (_lib.FLAG_DETERMINISTIC if MSDA._deterministic else 0) | (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE)
+        flags = (_lib.FLAG_DETERMINISTIC if MSDA.deterministic_enabled(value.dtype) else 0) | (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE)
         lib = _lib.load()
         code = _DTYPES[value.dtype]
         with torch.cuda.device(value.device):

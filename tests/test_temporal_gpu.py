@@ -218,3 +218,58 @@ def test_duplicate_frames_in_table_and_no_temporal_window():
     from oracle import msda_torch
     ref0 = msda_torch.msda_forward_torch(cpu("value"), torch.tensor(shapes), cpu("loc_curr"), cpu("aw_curr"))
     assert nmax(out0.cpu().numpy(), ref0.numpy()) < 1e-5
+
+
+def test_deterministic_mode_is_bit_reproducible_and_accurate():
+    """DEVIS_MSDA_FLAG_DETERMINISTIC: fixed-point integer accumulation of grad_value -- identical bits on every
+    run, and at least as close to the fp64 oracle as the default float-atomic mode."""
+    from devis_b200 import MultiScaleDeformableAttention as MSDA, synthetic
+    from oracle import temporal_torch
+    shapes = ((18, 30), (9, 15), (5, 8))
+    clip = synthetic.make_clip(n_frames=4, shapes=shapes, dist="local", seed=13, device="cuda")
+    _, grads_default, _ = _clip_fn(clip)
+    MSDA.set_deterministic(True)
+    try:
+        runs = [_clip_fn(clip)[1] for _ in range(3)]
+    finally:
+        MSDA.set_deterministic(False)
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)
+    cpu = {k: (v.detach().double().cpu() if isinstance(v, torch.Tensor) else v) for k, v in clip.items()}
+    leaves = [cpu[k].clone().requires_grad_(True) for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
+    offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(clip["frame_table"])]
+    ref = temporal_torch.temporal_core_per_frame(*leaves, torch.tensor(shapes), offs)
+    ref.backward(cpu["grad_out"])
+    want = leaves[0].grad.numpy()
+    err_det = nmax(runs[0][0].cpu().numpy(), want)
+    err_def = nmax(grads_default[0].cpu().numpy(), want)
+    assert err_det < 1e-4 and err_det <= err_def * 1.5 + 1e-7
+    # the other gradients do not depend on the mode
+    for a, b in zip(runs[0][1:], grads_default[1:]):
+        assert torch.equal(a, b)
+
+
+def test_deterministic_mode_drop_in_op_bf16_and_generic_channels():
+    from devis_b200 import MSDeformAttnFunction, MultiScaleDeformableAttention as MSDA
+    for name, dtype in (("op_d32", torch.bfloat16), ("op_d30", torch.float32), ("op_ragged", torch.float32)):
+        g = load_golden(name)
+        f = lambda k: torch.from_numpy(g[k]).cuda()
+        value, gout = f("value").to(dtype), f("gout").to(dtype)
+        loc, aw = f("loc").float(), f("aw").float()
+
+        def run():
+            v = value.clone().requires_grad_(True)
+            out = MSDeformAttnFunction.apply(v, f("shapes"), f("lsi"), loc, aw, 64)
+            out.backward(gout)
+            return v.grad
+        MSDA.set_deterministic(True)
+        try:
+            a, b = run(), run()
+        finally:
+            MSDA.set_deterministic(False)
+        assert torch.equal(a, b)
+        tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+        assert nmax(a.float().cpu().numpy(), g["gvalue"]) < tol
+    with torch.no_grad():
+        pass
