@@ -129,24 +129,28 @@ __global__ void __launch_bounds__(1024) k(const float *__restrict__ g, float *ou
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+static int g_grid = 148;
+
 template <int MODE>
 void run(const char *name, const float *g, float *out, float *red, long long *cyc, int threads)
 {
-    k<MODE><<<148, threads>>>(g, out, red, cyc);
+    cudaMemset(cyc, 0, 148 * 8);
+    k<MODE><<<g_grid, threads>>>(g, out, red, cyc);
     cudaDeviceSynchronize();
-    k<MODE><<<148, threads>>>(g, out, red, cyc);
+    k<MODE><<<g_grid, threads>>>(g, out, red, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[148];
     cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
     double avg = 0;
-    for (int i = 0; i < 148; ++i) avg += (double)h[i];
-    avg /= 148;
+    for (int i = 0; i < g_grid; ++i) avg += (double)h[i];
+    avg /= g_grid;
     const double per = avg / ((double)ITERS * (threads / 32));
-    printf("%-62s threads=%4d  %7.2f cyc / warp-instr   (%s)\n", name, threads, per, cudaGetErrorString(e));
+    printf("%-62s grid=%3d threads=%4d  %7.2f cyc / warp-instr   (%s)\n", name, g_grid, threads, per, cudaGetErrorString(e));
 }
 
-int main()
+int main(int argc, char **argv)
 {
+    const bool red_only = argc > 1;
     float *g, *out, *red;
     long long *cyc;
     const size_t n = (size_t)148 * ROWS * 32;
@@ -156,6 +160,15 @@ int main()
     cudaMalloc(&cyc, 148 * 8);
     cudaMemset(g, 0, n * 4);
     cudaMemset(red, 0, n * 4);
+    if (red_only) {
+        for (int grid : {8, 18, 37, 74, 148}) {
+            g_grid = grid;
+            run<11>("RED.128  8 lanes/row, 4 rows", g, out, red, cyc, 1024);
+            run<13>("RED.32   32 lanes, 1 row", g, out, red, cyc, 1024);
+            run<0>("LDG.128  4 full rows (L1 hits)", g, out, red, cyc, 1024);
+        }
+        return 0;
+    }
     for (int threads : {512, 1024}) {
         run<0>("LDG.128  8 lanes/row, 4 full rows        [value gather now]", g, out, red, cyc, threads);
         run<14>("LDG.128  all lanes same row (1 line)", g, out, red, cyc, threads);

@@ -273,3 +273,29 @@ def test_deterministic_mode_drop_in_op_bf16_and_generic_channels():
         assert nmax(a.float().cpu().numpy(), g["gvalue"]) < tol
     with torch.no_grad():
         pass
+
+
+def test_whole_clip_op_is_cuda_graph_capturable():
+    """launch-bound regime (decoder shapes): the op must be capturable so a layer can be replayed as a CUDA graph"""
+    from devis_b200 import clip_geometry, synthetic, temporal_ms_deform_attn
+    clip = synthetic.make_clip(queries=30, dist="uniform", seed=6, device="cuda")
+    geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
+    args = [clip[k] for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
+    eager = temporal_ms_deform_attn(*args, geom)
+    static_value = clip["value"].clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            temporal_ms_deform_attn(static_value, *args[1:], geom)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = temporal_ms_deform_attn(static_value, *args[1:], geom)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager)
+    static_value.mul_(2.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert nmax(static_out.cpu().numpy(), (2.0 * eager).cpu().numpy()) < 1e-6
