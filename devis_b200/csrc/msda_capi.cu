@@ -76,6 +76,31 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
     const int lpg = lanes_per_group(dtype, d);
+    // D = 32 with P % 4 == 0 in every segment can use 4 lanes x 8 channels with 16-byte tap records
+    // (msda_fwd8_kernel).  Measured at the DeVIS shape: bf16 -10 % (64-B rows: 0.75 instead of 1.0 data-pipe cycles per
+    // row), fp32 +-1 % local / +10 % uniform taps (LDG.256 costs 1.18 wavefronts per 128-B row against 1.01 for
+    // LDG.128, which eats what the smaller tap record saves) -> default: bf16 only.  Tuning key 4: 1 never, 2 always.
+    const int wide_mode = g_tuning[4].load();
+    bool wide = lpg == 8 && (wide_mode == 2 || (wide_mode == 0 && dtype == DEVIS_MSDA_BF16));
+    for (int sg = 0; sg < a.n_seg; ++sg) wide = wide && (a.seg[sg].P % 4 == 0);
+    if (wide) {
+        const LaunchShape s = pick_shape(d.Lq, 4, 0, 1);
+        smem += (size_t)(s.threads / 32) * Tap16::kBytesPerWarp;
+        const int qc = s.threads / 4;
+        const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
+        if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+        const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
+#define DEVIS_FWD8(BF, QPG) msda_fwd8_kernel<BF, QPG, SlotSrc><<<grid, s.threads, smem, st>>>(a)
+        if (dtype == DEVIS_MSDA_BF16) {
+            if (s.qpg == 2) DEVIS_FWD8(true, 2);
+            else DEVIS_FWD8(true, 1);
+        } else {
+            if (s.qpg == 2) DEVIS_FWD8(false, 2);
+            else DEVIS_FWD8(false, 1);
+        }
+#undef DEVIS_FWD8
+        return check_launch();
+    }
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, lpg, 0, 1);
         smem += exchange_bytes(lpg, s.threads);

@@ -133,4 +133,160 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
     }
 }
 
+
+// =================================================================================================
+// msda_fwd8_kernel -- D = 32 only: FOUR lanes per (query, head), 8 channels per lane.
+//
+// Round-1b profile + benchmarks/micro/l1_patterns.cu: the forward is bound by the SM's L1/shared data
+// pipe.  A gathered value row costs ~1.05 cycles however it is fetched (LDG.128 x 8 lanes, LDG.256 x 4
+// lanes, or LDS from a staged tile), so the only reducible cost is handing a tap's geometry to the lanes
+// that own its channels: every 32-bit word broadcast to a warp (SHFL or LDS) is one data-pipe wavefront.
+// This kernel halves the consumers per tap (4 lanes, 256-bit loads -- LDG.E.256 is new on sm_100) and
+// shrinks the record to ONE 16-byte LDS.128:  { TL byte offset | 4 flag bits,  w*hh,  w*lh,  lw }.
+//   flags: bit0 right column is a distinct row (else clamped onto the left one), bit1 bottom row distinct,
+//          bit2 left column inside the map, bit3 right column inside the map;
+//   hw = 1 - lw is recomputed (bit-identical to the producer's), the other three corner offsets follow
+//   from TL, the flags and the slot's row pitch.  Requires P % 4 == 0 so that the 4 taps a group
+//   exchanges at a time belong to one slot (DeVIS: P = 4 everywhere, config.py:52-53,108-109).
+// For bf16 value a head's row is 64 B = 4 lanes x 16 B: 8 rows per LDG.128, measured 0.75 cycles/row
+// against 1.0 for the 8-lane x 8-byte mapping.
+// =================================================================================================
+struct Tap16 {
+    static constexpr int kWordsPerWarpBuf = 4 * 8 * 4;  // 4 taps x 8 groups x 4 words
+    static constexpr int kBytesPerWarp = 2 * kWordsPerWarpBuf * 4;
+    __device__ static __forceinline__ int word(int j, int g) { return (j * 8 + (g ^ (2 * j))) * 4; }
+};
+
+__device__ __forceinline__ void ldg_f8(const char *p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ void ldg_bf16x8(const char *p, float (&v)[8])
+{
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    v[0] = __uint_as_float(r.x << 16);
+    v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16);
+    v[3] = __uint_as_float(r.y & 0xffff0000u);
+    v[4] = __uint_as_float(r.z << 16);
+    v[5] = __uint_as_float(r.z & 0xffff0000u);
+    v[6] = __uint_as_float(r.w << 16);
+    v[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+
+template <bool BF16, int QPG, class SlotSrc>
+__global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a)
+{
+    constexpr int LPG = 4;
+    extern __shared__ int4 s_slot[];
+    const int outer = blockIdx.y;
+    build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16::kWordsPerWarpBuf);
+
+    const int M = a.d.M, Lq = a.d.Lq;
+    const int j = threadIdx.x & 3;            // 8-channel slice owned by this lane == tap it prepares
+    const int g = (threadIdx.x & 31) >> 2;    // group within the warp (8 groups)
+    const int grp = threadIdx.x >> 2;         // group within the CTA
+    const int QC = blockDim.x >> 2;
+    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+
+    int q[QPG];
+    bool qlive[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        const int qi = (qchunk * QPG + i) * QC + grp;
+        qlive[i] = qi < Lq;
+        q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
+    }
+
+    constexpr unsigned kLaneBytes = BF16 ? 16u : 32u;      // 8 channels
+    const unsigned rowbytes = (unsigned)(M * LPG) * kLaneBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kLaneBytes;
+    asm volatile("" : "+l"(vbase));   // keep base as one 64-bit register pair (see msda_fwd_kernel)
+
+    float acc[QPG][8];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+
+    int slot_base = 0, parity = 0;
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;   // P % 4 == 0 (checked by the launcher)
+        const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
+        const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
+        for (int k0 = 0; k0 < K; k0 += LPG) {
+            const int k = k0 + j;                                // always < K
+            const int4 sl = s_slot[slot_base + k0 / P];          // one slot for the whole exchange
+            const unsigned pitch = (unsigned)sl.y * rowbytes;    // bytes between vertically adjacent rows
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) {
+                const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+                float2 xy = make_float2(0.f, 0.f);
+                float w = 0.f;
+                if (qlive[i]) {
+                    xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                    w = __ldg(aw + row * K + k);
+                }
+                const TapGeom t = tap_geometry(xy.x, xy.y, sl, qlive[i]);
+                uint4 rec;
+                rec.x = (unsigned)t.rTL * rowbytes | (unsigned)(t.rTR != t.rTL) | ((unsigned)(t.rBL != t.rTL) << 1) |
+                        (t.ok & 4u) | (t.ok & 8u);
+                rec.y = __float_as_uint((t.ok & 1u) ? w * t.hh : 0.f);
+                rec.z = __float_as_uint((t.ok & 2u) ? w * t.lh : 0.f);
+                rec.w = __float_as_uint(t.lw);
+                float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
+                parity ^= 1;
+                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = rec;
+                __syncwarp();
+#pragma unroll
+                for (int jj = 0; jj < LPG; ++jj) {
+                    const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
+                    const unsigned oTL = r.x & ~15u;
+                    const unsigned dcol = (r.x & 1u) ? rowbytes : 0u, drow = (r.x & 2u) ? pitch : 0u;
+                    const unsigned oTR = oTL + dcol, oBL = oTL + drow, oBR = oBL + dcol;
+                    const float lw = __uint_as_float(r.w);
+                    const float hwm = (r.x & 4u) ? 1.f - lw : 0.f, lwm = (r.x & 8u) ? lw : 0.f;
+                    const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
+                    const float c00 = whh * hwm, c01 = whh * lwm, c10 = wlh * hwm, c11 = wlh * lwm;
+                    float v00[8], v01[8], v10[8], v11[8];
+                    if (BF16) {
+                        ldg_bf16x8(vbase + oTL, v00);
+                        ldg_bf16x8(vbase + oTR, v01);
+                        ldg_bf16x8(vbase + oBL, v10);
+                        ldg_bf16x8(vbase + oBR, v11);
+                    } else {
+                        ldg_f8(vbase + oTL, v00);
+                        ldg_f8(vbase + oTR, v01);
+                        ldg_f8(vbase + oBL, v10);
+                        ldg_f8(vbase + oBR, v11);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        acc[i][c] = fmaf(c11, v11[c], fmaf(c10, v10[c], fmaf(c01, v01[c], fmaf(c00, v00[c], acc[i][c]))));
+                }
+            }
+        }
+        slot_base += a.seg[sg].n_slots;
+    }
+
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        if (!qlive[i]) continue;
+        const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+        if (BF16) {
+            const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+            reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+            float4 *o = reinterpret_cast<float4 *>(a.out) + (row * LPG + j) * 2;
+            o[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            o[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+    }
+}
+
 }  // namespace devis

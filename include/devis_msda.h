@@ -66,7 +66,8 @@ int devis_msda_last_cuda_error(void);
 uint64_t devis_msda_launch_count(void);
 /* Launch-shape knobs for benchmarking (process-wide; 0 restores the built-in heuristic).
  * key 0: forward threads per block, 1: forward queries per lane group,
- * key 2: backward threads per block, 3: backward queries per lane group. */
+ * key 2: backward threads per block, 3: backward queries per lane group,
+ * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always (A/B testing). */
 int devis_msda_set_tuning(int key, int value);
 
 /*
