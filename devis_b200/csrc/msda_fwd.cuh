@@ -20,6 +20,15 @@
 #pragma once
 #include "msda_common.cuh"
 
+#ifndef DEVIS_FWD_TAP_BATCH
+#define DEVIS_FWD_TAP_BATCH 2
+#endif
+// 3 blocks of 256 threads per SM caps the kernel at 80 registers; without a cap ptxas hoists all 32 corner loads of
+// an 8-tap exchange (182 registers, 1 block/SM: 787 us instead of 580 us at the DeVIS shape)
+#ifndef DEVIS_FWD_MIN_BLOCKS
+#define DEVIS_FWD_MIN_BLOCKS 3
+#endif
+
 namespace devis {
 
 template <class SlotSrc>
@@ -35,7 +44,7 @@ struct FwdArgs {
 };
 
 template <bool BF16, int LPG, int QPG, class SlotSrc>
-__global__ void __launch_bounds__(256) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
+__global__ void __launch_bounds__(256, DEVIS_FWD_MIN_BLOCKS) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
 {
     using X = TapExchange<LPG>;
     extern __shared__ int4 s_slot[];
@@ -95,27 +104,36 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const FwdArgs<SlotSrc> a)
                 parity ^= 1;
                 X::publish(buf, j, g, t, w, rowbytes);
                 __syncwarp();
+                // TB taps are fetched together so that 4*TB corner loads are in flight before the first FFMA needs one
+                constexpr int TB = DEVIS_FWD_TAP_BATCH;
 #pragma unroll
-                for (int jj = 0; jj < LPG; ++jj) {
-                    uint4 off;
-                    float4 c;
-                    X::fetch(buf, jj, g, off, c);
-                    float4 v00, v01, v10, v11;
-                    if (BF16) {
-                        v00 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.x));
-                        v01 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.y));
-                        v10 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.z));
-                        v11 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.w));
-                    } else {
-                        v00 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.x));
-                        v01 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.y));
-                        v10 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.z));
-                        v11 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.w));
+                for (int j0 = 0; j0 < LPG; j0 += TB) {
+                    uint4 off[TB];
+                    float4 c[TB];
+                    float4 v[TB][4];
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) X::fetch(buf, j0 + u, g, off[u], c[u]);
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) {
+                        if (BF16) {
+                            v[u][0] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].x));
+                            v[u][1] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].y));
+                            v[u][2] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].z));
+                            v[u][3] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].w));
+                        } else {
+                            v[u][0] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].x));
+                            v[u][1] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].y));
+                            v[u][2] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].z));
+                            v[u][3] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].w));
+                        }
                     }
-                    acc[i].x = fmaf(c.w, v11.x, fmaf(c.z, v10.x, fmaf(c.y, v01.x, fmaf(c.x, v00.x, acc[i].x))));
-                    acc[i].y = fmaf(c.w, v11.y, fmaf(c.z, v10.y, fmaf(c.y, v01.y, fmaf(c.x, v00.y, acc[i].y))));
-                    acc[i].z = fmaf(c.w, v11.z, fmaf(c.z, v10.z, fmaf(c.y, v01.z, fmaf(c.x, v00.z, acc[i].z))));
-                    acc[i].w = fmaf(c.w, v11.w, fmaf(c.z, v10.w, fmaf(c.y, v01.w, fmaf(c.x, v00.w, acc[i].w))));
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) {
+                        acc[i].x = fmaf(c[u].w, v[u][3].x, fmaf(c[u].z, v[u][2].x, fmaf(c[u].y, v[u][1].x, fmaf(c[u].x, v[u][0].x, acc[i].x))));
+                        acc[i].y = fmaf(c[u].w, v[u][3].y, fmaf(c[u].z, v[u][2].y, fmaf(c[u].y, v[u][1].y, fmaf(c[u].x, v[u][0].y, acc[i].y))));
+                        acc[i].z = fmaf(c[u].w, v[u][3].z, fmaf(c[u].z, v[u][2].z, fmaf(c[u].y, v[u][1].z, fmaf(c[u].x, v[u][0].z, acc[i].z))));
+                        acc[i].w = fmaf(c[u].w, v[u][3].w, fmaf(c[u].z, v[u][2].w, fmaf(c[u].y, v[u][1].w, fmaf(c[u].x, v[u][0].w, acc[i].w))));
+                    }
                 }
             }
         }
