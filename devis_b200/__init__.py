@@ -12,10 +12,11 @@ There is no CPU or PyTorch fallback: the ops raise if libdevis_msda.so is absent
 """
 from . import _lib, clip_geometry  # noqa: F401
 from . import MultiScaleDeformableAttention  # noqa: F401
-from .functions import MSDeformAttnFunction, TemporalMSDeformAttnFunction, temporal_ms_deform_attn  # noqa: F401
+from .functions import (MSDeformAttnFunction, TemporalMSDeformAttnFunction,  # noqa: F401
+                        TemporalMSDeformAttnFusedFunction, temporal_ms_deform_attn)
 from .modules import (MSDeformAttn, TemporalMSDeformAttnBase, TemporalMSDeformAttnDecoder,  # noqa: F401
                       TemporalMSDeformAttnEncoder)
 
-__all__ = ["MSDeformAttnFunction", "TemporalMSDeformAttnFunction", "temporal_ms_deform_attn", "MSDeformAttn",
+__all__ = ["MSDeformAttnFunction", "TemporalMSDeformAttnFunction", "TemporalMSDeformAttnFusedFunction", "temporal_ms_deform_attn", "MSDeformAttn",
            "TemporalMSDeformAttnBase", "TemporalMSDeformAttnEncoder", "TemporalMSDeformAttnDecoder",
            "MultiScaleDeformableAttention", "clip_geometry"]

@@ -31,6 +31,8 @@ SIGNATURES = {
     "devis_tmsda_forward": (_i, [_vp] * 10 + [_i] * 10 + [_vp]),
     "devis_tmsda_backward_workspace_bytes": (_sz, [_i] * 10 + [_u]),
     "devis_tmsda_backward": (_i, [_vp] * 15 + [_i] * 10 + [_u, _vp, _sz, _vp]),
+    "devis_tmsda_fused_forward": (_i, [_vp] * 11 + [_i] * 10 + [_vp]),
+    "devis_tmsda_fused_backward": (_i, [_vp] * 16 + [_i] * 10 + [_u, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 #include "msda_common.cuh"
 #include "msda_fwd.cuh"
 #include "msda_generic.cuh"
+#include "tmsda_fused.cuh"
 
 using namespace devis;
 
@@ -439,6 +440,122 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
     a.q_perm = query_order;
     return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, const int64_t *lsi, const int32_t *frames,
+                      const void *ref, const void *off_c, const void *logit_c, const void *off_t, const void *logit_t,
+                      const int32_t *order, int T, int S, int M, int D, int L, int Lq, int Pc, int Pt, int Wt, int dtype)
+{
+    int rc = check_common(T, S, M, D, L, Lq, dtype);
+    if (rc) return rc;
+    if (Pc <= 0 || Pt < 0 || Wt < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (dtype == DEVIS_MSDA_F64 || D != 32) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    if ((unsigned long long)T * S * M * D * elem_size(dtype) >= (1ull << 32)) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const bool temporal = Wt > 0 && Pt > 0;
+    if (!shapes || !lsi || (temporal && !frames)) return DEVIS_MSDA_ERR_NULL_POINTER;
+    const bool empty = T == 0 || Lq == 0;
+    if (!empty && (!value || !ref || !off_c || !logit_c || (temporal && (!off_t || !logit_t))))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    rc = fill_clip_table(a.src, shapes, lsi, frames, T, S, L, temporal ? Wt : 0);
+    if (rc) return rc;
+    a.value = value;
+    a.ref = reinterpret_cast<const float *>(ref);
+    a.off[0] = reinterpret_cast<const float *>(off_c);
+    a.logit[0] = reinterpret_cast<const float *>(logit_c);
+    a.off[1] = reinterpret_cast<const float *>(off_t);
+    a.logit[1] = reinterpret_cast<const float *>(logit_t);
+    a.n_slots[0] = L;
+    a.P[0] = Pc;
+    a.n_slots[1] = temporal ? Wt * L : 0;
+    a.P[1] = temporal ? Pt : 1;
+    a.n_seg = temporal ? 2 : 1;
+    if (a.n_slots[0] + a.n_slots[1] > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
+    a.d = OpDims{T, S, M, D, Lq};
+    a.q_perm = order;
+    return DEVIS_MSDA_OK;
+}
+
+static int fused_grid(const FusedArgs &a, int key_threads, dim3 &grid, int &threads, size_t &smem)
+{
+    threads = g_tuning[key_threads].load();
+    if (threads == 0) threads = a.d.Lq >= 1024 ? 256 : a.d.Lq >= 128 ? 128 : 64;
+    threads = threads < 32 ? 32 : threads > 256 ? 256 : (threads / 32) * 32;
+    const long long chunks = ((long long)a.d.Lq + threads / 8 - 1) / (threads / 8);
+    if (chunks * a.d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    grid = dim3((unsigned)(chunks * a.d.M), (unsigned)a.d.outer);
+    smem = (size_t)(a.n_slots[0] + a.n_slots[1]) * sizeof(int4) + exchange_bytes(8, threads);
+    return DEVIS_MSDA_OK;
+}
+
+int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_host,
+                              const int64_t *level_start_index_host, const int32_t *frame_table_host,
+                              const void *ref, const void *off_curr, const void *logit_curr,
+                              const void *off_temporal, const void *logit_temporal, void *output,
+                              const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
+                              int channels, int num_levels, int num_query, int n_curr_points,
+                              int n_temporal_points, int t_window, int dtype, void *stream)
+{
+    FusedArgs a{};
+    int rc = fill_fused(a, value, spatial_shapes_host, level_start_index_host, frame_table_host, ref, off_curr,
+                        logit_curr, off_temporal, logit_temporal, query_order, num_frames, spatial_size, num_heads,
+                        channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, dtype);
+    if (rc) return rc;
+    if (num_frames == 0 || num_query == 0) return DEVIS_MSDA_OK;
+    if (!output) return DEVIS_MSDA_ERR_NULL_POINTER;
+    a.out = output;
+    dim3 grid;
+    int threads;
+    size_t smem;
+    rc = fused_grid(a, 0, grid, threads, smem);
+    if (rc) return rc;
+    if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    else tmsda_fused_fwd_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    return check_launch();
+}
+
+int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_host,
+                               const int64_t *level_start_index_host, const int32_t *frame_table_host,
+                               const void *ref, const void *off_curr, const void *logit_curr,
+                               const void *off_temporal, const void *logit_temporal, const void *grad_output,
+                               void *grad_value, void *grad_off_curr, void *grad_logit_curr,
+                               void *grad_off_temporal, void *grad_logit_temporal, const int32_t *query_order,
+                               int num_frames, int spatial_size, int num_heads, int channels, int num_levels,
+                               int num_query, int n_curr_points, int n_temporal_points, int t_window, int dtype,
+                               unsigned flags, void *stream)
+{
+    FusedArgs a{};
+    int rc = fill_fused(a, value, spatial_shapes_host, level_start_index_host, frame_table_host, ref, off_curr,
+                        logit_curr, off_temporal, logit_temporal, query_order, num_frames, spatial_size, num_heads,
+                        channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, dtype);
+    if (rc) return rc;
+    if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (want_gv) {
+        const size_t bytes = (size_t)num_frames * spatial_size * num_heads * channels * sizeof(float);
+        if (bytes && !grad_value) return DEVIS_MSDA_ERR_NULL_POINTER;
+        if (bytes) {
+            const cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, st);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+    }
+    if (num_frames == 0 || num_query == 0) return DEVIS_MSDA_OK;
+    if (!grad_output || !grad_off_curr || !grad_logit_curr || (a.n_seg > 1 && (!grad_off_temporal || !grad_logit_temporal)))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    a.grad_out = grad_output;
+    a.grad_value = want_gv ? reinterpret_cast<float *>(grad_value) : nullptr;
+    a.grad_off[0] = reinterpret_cast<float *>(grad_off_curr);
+    a.grad_logit[0] = reinterpret_cast<float *>(grad_logit_curr);
+    a.grad_off[1] = reinterpret_cast<float *>(grad_off_temporal);
+    a.grad_logit[1] = reinterpret_cast<float *>(grad_logit_temporal);
+    dim3 grid;
+    int threads;
+    size_t smem;
+    rc = fused_grid(a, 2, grid, threads, smem);
+    if (rc) return rc;
+    if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
+    else tmsda_fused_bwd_kernel<false><<<grid, threads, smem, st>>>(a);
+    return check_launch();
 }
 
 }  // extern "C"

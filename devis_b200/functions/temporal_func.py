@@ -117,6 +117,73 @@ class TemporalMSDeformAttnFunction(Function):
         return gv, glc, gac, glt, gat, None, None
 
 
+class TemporalMSDeformAttnFusedFunction(Function):
+    """apply(value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None) -> (T, Lq, M*D)
+
+    Whole-clip temporal attention straight from the Linear outputs (encoder form): the joint softmax over all taps
+    and ``ref + off / (W, H)`` (ms_deform_attn.py:240-260, 437-452) happen inside the kernels, and the backward returns
+    the gradients of the raw offsets and logits.  value (T,S,M,32) fp32|bf16; ref (T,Lq,L,2); off_curr
+    (T,Lq,M,L,Pc,2); logit_curr (T,Lq,M,L*Pc); off_temporal (T,Lq,M,Wt*L,Pt,2); logit_temporal (T,Lq,M,Wt*L*Pt)."""
+
+    @staticmethod
+    def supported(like, head_dim, reference_points):
+        """`like`: a tensor with value's device, dtype and element count (e.g. the module's input_flatten)"""
+        return (like.is_cuda and like.dtype in (torch.float32, torch.bfloat16) and head_dim == 32
+                and reference_points.shape[-1] == 2 and like.numel() * like.element_size() < (1 << 32)
+                and not MSDA.deterministic_enabled(like.dtype))
+
+    @staticmethod
+    def forward(ctx, value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None):
+        f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
+        value = value if value.is_contiguous() else value.contiguous()
+        ref, oc, lc = f32(ref), f32(off_curr), f32(logit_curr)
+        has_t = geometry.t_window > 0 and off_temporal is not None
+        ot = f32(off_temporal) if has_t else None
+        lt = f32(logit_temporal) if has_t else None
+        t, s, m, d = value.shape
+        lq, pc = oc.shape[1], oc.shape[4]
+        pt = ot.shape[4] if has_t else 0
+        if t != geometry.n_frames or s != geometry.spatial_size or oc.shape[3] != geometry.n_levels:
+            raise RuntimeError("operands do not match the clip geometry")
+        out = torch.empty((t, lq, m * d), dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            _lib.check(_lib.load().devis_tmsda_fused_forward(
+                _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr, _ptr(ref), _ptr(oc), _ptr(lc),
+                _ptr(ot), _ptr(lt), _ptr(out), _ptr(query_order), t, s, m, d, geometry.n_levels, lq, pc, pt,
+                geometry.t_window if has_t else 0, _DTYPES[value.dtype], torch.cuda.current_stream().cuda_stream))
+        ctx.geometry, ctx.has_t = geometry, has_t
+        ctx.dims = (t, s, m, d, lq, pc, pt)
+        ctx.in_dtypes = (off_curr.dtype, logit_curr.dtype, off_temporal.dtype if has_t else None,
+                         logit_temporal.dtype if has_t else None)
+        ctx.save_for_backward(value, ref, oc, lc, ot, lt, query_order)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, ref, oc, lc, ot, lt, query_order = ctx.saved_tensors
+        geometry, has_t = ctx.geometry, ctx.has_t
+        t, s, m, d, lq, pc, pt = ctx.dims
+        gout = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
+        gout = gout if gout.is_contiguous() else gout.contiguous()
+        need_gv = ctx.needs_input_grad[0]
+        gv = torch.empty(value.shape, dtype=torch.float32, device=value.device) if need_gv else None
+        goc, glc = torch.empty_like(oc), torch.empty_like(lc)
+        got = torch.empty_like(ot) if has_t else None
+        glt = torch.empty_like(lt) if has_t else None
+        with torch.cuda.device(value.device):
+            _lib.check(_lib.load().devis_tmsda_fused_backward(
+                _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr, _ptr(ref), _ptr(oc), _ptr(lc),
+                _ptr(ot), _ptr(lt), _ptr(gout), _ptr(gv), _ptr(goc), _ptr(glc), _ptr(got), _ptr(glt), _ptr(query_order),
+                t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0, _DTYPES[value.dtype],
+                0 if need_gv else _lib.FLAG_NO_GRAD_VALUE, torch.cuda.current_stream().cuda_stream))
+        doc, dlc, dot, dlt = ctx.in_dtypes
+        if gv is not None and gv.dtype != value.dtype:
+            gv = gv.to(value.dtype)
+        cast = lambda g, dt: g if (g is None or g.dtype == dt) else g.to(dt)
+        return gv, None, cast(goc, doc), cast(glc, dlc), cast(got, dot), cast(glt, dlt), None, None
+
+
 def temporal_ms_deform_attn(value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry, query_order=None):
     return TemporalMSDeformAttnFunction.apply(value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry,
                                               query_order)

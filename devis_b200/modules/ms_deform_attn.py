@@ -21,7 +21,7 @@ from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
 from .. import clip_geometry
-from ..functions import MSDeformAttnFunction, temporal_ms_deform_attn
+from ..functions import MSDeformAttnFunction, TemporalMSDeformAttnFusedFunction, temporal_ms_deform_attn
 
 
 def _is_power_of_2(n):
@@ -126,6 +126,8 @@ class TemporalMSDeformAttnBase(nn.Module):
         self.output_proj = nn.Linear(d_model, d_model)
         # encoder only: walk the pixel-grid queries in 2-D tiles (cache locality, see ClipGeometry.tile_order)
         self.query_tile = (8, 8)
+        # encoder only: let the kernels read the raw Linear outputs (joint softmax and `ref + off / (W, H)` fused in)
+        self.fuse_prologue = True
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -180,6 +182,24 @@ class TemporalMSDeformAttnEncoder(TemporalMSDeformAttnBase):
         n_frames = input_flatten.shape[0]
         assert reference_points.shape[-1] == 2
         geom = self._geometry(n_frames, input_spatial_shapes, input_level_start_index, temporal_offsets)
+        order = None
+        if self.query_tile and query.shape[1] == geom.spatial_size:
+            order = geom.tile_order(query.device, *self.query_tile)
+
+        if self.fuse_prologue and TemporalMSDeformAttnFusedFunction.supported(
+                input_flatten, self.d_model // self.n_heads, reference_points):
+            t, lq, _ = query.shape
+            m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
+            value = self.value_proj(input_flatten).view(t, input_flatten.shape[1], m, self.d_model // m)
+            if True:
+                out = TemporalMSDeformAttnFusedFunction.apply(
+                    value, reference_points,
+                    self.sampling_offsets(query).view(t, lq, m, nl, pc, 2),
+                    self.attention_weights(query).view(t, lq, m, nl * pc),
+                    self.temporal_sampling_offsets(query).view(t, lq, m, wt * nl, pt, 2),
+                    self.temporal_attention_weights(query).view(t, lq, m, wt * nl * pt), geom, order)
+                return self.output_proj(out), None
+
         value, off_c, off_t, aw_c, aw_t = self._compute_deformable_attention(query, input_flatten)
 
         wh = _wh(cur_shapes, off_c.dtype)
@@ -188,9 +208,6 @@ class TemporalMSDeformAttnEncoder(TemporalMSDeformAttnBase):
         loc_t = reference_points[:, :, 0][:, :, None, None, None, :] \
             + off_t / wh.repeat(self.t_window, 1)[None, None, None, :, None, :]
 
-        order = None
-        if self.query_tile and query.shape[1] == geom.spatial_size:
-            order = geom.tile_order(query.device, *self.query_tile)
         out = temporal_ms_deform_attn(value, loc_c, aw_c, loc_t, aw_t, geom, order)
         return self.output_proj(out), None
 

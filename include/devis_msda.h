@@ -143,6 +143,37 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
                          int n_temporal_points, int t_window, int dtype, unsigned flags, void *workspace,
                          size_t workspace_bytes, void *stream);
 
+/*
+ * Whole-clip temporal attention with the prologue fused in (encoder form).  Replaces, besides the per-frame op calls,
+ * the elementwise chain that turns the Linear outputs into op operands: the cat + joint softmax over all
+ * K = L*Pc + Wt*L*Pt taps (modules/ms_deform_attn.py:240-260) and `ref + off / (W, H)` for current and temporal taps
+ * (:437-439, :447-452; temporal taps start from the LEVEL-0 reference point).
+ *   ref            (num_frames, num_query, num_levels, 2) float   reference points (x, y), no gradient
+ *   off_curr       (num_frames, num_query, num_heads, num_levels, n_curr_points, 2) float      raw sampling_offsets output
+ *   logit_curr     (num_frames, num_query, num_heads, num_levels*n_curr_points) float           raw attention_weights output
+ *   off_temporal   (num_frames, num_query, num_heads, t_window*num_levels, n_temporal_points, 2) float
+ *   logit_temporal (num_frames, num_query, num_heads, t_window*num_levels*n_temporal_points) float
+ * value / output / grad_output: DEVIS_MSDA_F32 or DEVIS_MSDA_BF16; channels must be 32 (else DEVIS_MSDA_ERR_UNSUPPORTED
+ * and the caller uses devis_tmsda_forward on materialised operands).  The backward writes d/d(off_*) and d/d(logit_*)
+ * directly; grad_value (float) is zero-filled by the call; flags: DEVIS_MSDA_FLAG_NO_GRAD_VALUE only.
+ */
+int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_host,
+                              const int64_t *level_start_index_host, const int32_t *frame_table_host,
+                              const void *ref, const void *off_curr, const void *logit_curr,
+                              const void *off_temporal, const void *logit_temporal, void *output,
+                              const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
+                              int channels, int num_levels, int num_query, int n_curr_points,
+                              int n_temporal_points, int t_window, int dtype, void *stream);
+int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_host,
+                               const int64_t *level_start_index_host, const int32_t *frame_table_host,
+                               const void *ref, const void *off_curr, const void *logit_curr,
+                               const void *off_temporal, const void *logit_temporal, const void *grad_output,
+                               void *grad_value, void *grad_off_curr, void *grad_logit_curr,
+                               void *grad_off_temporal, void *grad_logit_temporal, const int32_t *query_order,
+                               int num_frames, int spatial_size, int num_heads, int channels, int num_levels,
+                               int num_query, int n_curr_points, int n_temporal_points, int t_window, int dtype,
+                               unsigned flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,3 +299,83 @@ def test_whole_clip_op_is_cuda_graph_capturable():
     graph.replay()
     torch.cuda.synchronize()
     assert nmax(static_out.cpu().numpy(), (2.0 * eager).cpu().numpy()) < 1e-6
+
+
+def test_fused_prologue_matches_unfused_path_and_reference_module():
+    """TemporalMSDeformAttnFusedFunction (softmax + location arithmetic inside the kernels) against the unfused module
+    path at the full DeVIS encoder shape, forward and every gradient; and against the golden reference-module fixture
+    (fp32; its d_model/heads give D = 8, which the fused kernels do not serve -> must fall back, same numbers)."""
+    from devis_b200 import TemporalMSDeformAttnEncoder, synthetic
+    torch.manual_seed(0)
+    T, shapes_l = 6, synthetic.DEVIS_SHAPES
+    S = sum(h * w for h, w in shapes_l)
+    enc = TemporalMSDeformAttnEncoder(n_frames=T, d_model=256, n_levels=4, t_window=T - 1, n_heads=8, n_curr_points=4,
+                                      n_temporal_points=4).cuda()
+    with torch.no_grad():
+        for lin in (enc.sampling_offsets, enc.temporal_sampling_offsets, enc.attention_weights, enc.temporal_attention_weights):
+            lin.weight.normal_(0, 0.05)
+    query = torch.randn(T, S, 256, device="cuda")
+    inp = torch.randn(T, S, 256, device="cuda")
+    ref = synthetic.pixel_reference_points(shapes_l, T, "cuda")
+    shapes = torch.tensor(shapes_l, device="cuda")
+    lsi = torch.tensor(synthetic.level_start_index(shapes_l), device="cuda")
+    tshapes = shapes.repeat(T - 1, 1)
+    tlsi = torch.cat([tshapes.new_zeros(1), tshapes.prod(1).cumsum(0)[:-1]])
+    offsets = [torch.tensor([d for d in range(-t, T - t) if d != 0], device="cuda") for t in range(T)]
+    gout = torch.randn(T, S, 256, device="cuda")
+    results = {}
+    for fused in (True, False):
+        enc.fuse_prologue = fused
+        enc.zero_grad(set_to_none=True)
+        q = query.clone().requires_grad_(True)
+        x = inp.clone().requires_grad_(True)
+        out, _ = enc(q, ref, x, (shapes, tshapes), (lsi, tlsi), offsets)
+        out.backward(gout)
+        results[fused] = (out.detach(), q.grad, x.grad, {n: p.grad.clone() for n, p in enc.named_parameters()})
+    f, u = results[True], results[False]
+    assert nmax(f[0].cpu().numpy(), u[0].cpu().numpy()) < 1e-5
+    assert nmax(f[1].cpu().numpy(), u[1].cpu().numpy()) < 2e-4
+    assert nmax(f[2].cpu().numpy(), u[2].cpu().numpy()) < 2e-4
+    for name in f[3]:
+        assert nmax(f[3][name].cpu().numpy(), u[3][name].cpu().numpy()) < 2e-4, name
+
+
+def test_fused_function_matches_pytorch_oracle_on_small_clip():
+    """fused op vs the fp64 PyTorch oracle (projection-free): logits/offsets -> softmax/locations -> per-frame loop"""
+    from devis_b200 import TemporalMSDeformAttnFusedFunction, clip_geometry, synthetic
+    from oracle import temporal_torch
+    torch.manual_seed(1)
+    shapes_l, T, M, D, pc, pt = ((18, 30), (9, 15), (5, 8)), 4, 8, 32, 4, 4
+    nl, wt = len(shapes_l), T - 1
+    S = sum(h * w for h, w in shapes_l)
+    geom = clip_geometry.ClipGeometry(shapes_l, T, clip_geometry.all_frames_table(T))
+    ref = synthetic.pixel_reference_points(shapes_l, T, "cuda")
+    value = torch.randn(T, S, M, D, device="cuda")
+    # offsets in pixels, kept away from cell borders by construction of the oracle comparison tolerance
+    off_c = (2.0 * torch.randn(T, S, M, nl, pc, 2, device="cuda")).requires_grad_(True)
+    off_t = (2.0 * torch.randn(T, S, M, wt * nl, pt, 2, device="cuda")).requires_grad_(True)
+    lg_c = torch.randn(T, S, M, nl * pc, device="cuda").requires_grad_(True)
+    lg_t = torch.randn(T, S, M, wt * nl * pt, device="cuda").requires_grad_(True)
+    v = value.clone().requires_grad_(True)
+    out = TemporalMSDeformAttnFusedFunction.apply(v, ref, off_c, lg_c, off_t, lg_t, geom, geom.tile_order("cuda"))
+    gout = torch.randn_like(out)
+    out.backward(gout)
+
+    d = lambda t: t.detach().double().cpu()
+    shapes = torch.tensor(shapes_l)
+    o_c, o_t, l_c, l_t, vv = (d(x).requires_grad_(True) for x in (off_c, off_t, lg_c, lg_t, value))
+    joint = torch.softmax(torch.cat([l_c, l_t], -1), -1)
+    aw_c = joint[..., :nl * pc].reshape(T, S, M, nl, pc)
+    aw_t = joint[..., nl * pc:].reshape(T, S, M, wt * nl, pt)
+    loc_c, loc_t = temporal_torch.encoder_locations(d(ref), o_c, o_t, shapes, wt)
+    offs = temporal_torch.all_frames_offsets(T)
+    want = temporal_torch.temporal_core_per_frame(vv, loc_c, aw_c, loc_t, aw_t, shapes, offs)
+    want.backward(d(gout))
+    assert nmax(out.detach().cpu().numpy(), want.detach().numpy()) < 1e-5
+    # taps are not boundary-safe here (raw random offsets): gate location gradients on a quantile, others on max
+    assert nmax(v.grad.cpu().numpy(), vv.grad.numpy()) < 1e-4
+    assert nmax(lg_c.grad.cpu().numpy(), l_c.grad.numpy()) < 1e-4
+    assert nmax(lg_t.grad.cpu().numpy(), l_t.grad.numpy()) < 1e-4
+    for got, ref_g in ((off_c.grad, o_c.grad), (off_t.grad, o_t.grad)):
+        err = (got.double().cpu() - ref_g).abs() / ref_g.abs().max()
+        assert torch.quantile(err.flatten()[:2_000_000], 0.999) < 1e-4
