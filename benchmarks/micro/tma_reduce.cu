@@ -29,10 +29,15 @@ __global__ void __launch_bounds__(1024) k(float *redbuf, long long *cycles, int 
     for (int it = 0; it < ITERS; ++it) {
         s8 = s8 * 1664525u + 1013904223u;
         const unsigned row = (s8 >> 9) % (ROWS - 1);
+        if (MODE == 3) {   // both paths in the same iteration: REDG for one row, TMA bulk reduce for another
+            float *p = base + (size_t)row * 32 + j * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
+        }
         if (MODE == 0) {
             float *p = base + (size_t)row * 32 + j * 4;
             asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
         } else {
+            const unsigned row = (MODE == 3) ? ((s8 >> 5) % (ROWS - 1)) : ((s8 >> 9) % (ROWS - 1));
             const int slot = it % DEPTH;
             if (it >= DEPTH && j == 0) {   // the staging row is reused: wait until at most DEPTH-1 groups are pending
                 asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DEPTH - 1) : "memory");
@@ -71,7 +76,7 @@ void run(const char *name, float *red, long long *cyc, int threads, int grid, in
     double avg = 0;
     for (int i = 0; i < grid; ++i) avg += (double)h[i];
     avg /= grid;
-    const double rows = (double)ITERS * (threads / 32) * 4 * (bytes / 128);
+    const double rows = (double)ITERS * (threads / 32) * 4 * (bytes / 128) * (MODE == 3 ? 2 : 1);
     printf("%-58s grid=%3d threads=%4d depth=%d  %6.2f cyc per 128-B row per SM  (%s)\n", name, grid, threads, DEPTH,
            avg / rows, cudaGetErrorString(e));
 }
@@ -84,12 +89,13 @@ int main()
     cudaMalloc(&cyc, 148 * 8);
     cudaMemset(red, 0, (size_t)148 * ROWS * 32 * 4);
     for (int grid : {16, 148}) {
-        for (int threads : {256, 512}) {
+        for (int threads : {512, 1024}) {
             run<0, 1>("REDG v4.f32, 4 rows / warp instr", red, cyc, threads, grid, 128);
             run<1, 2>("TMA bulk reduce add.f32, 128 B per op", red, cyc, threads, grid, 128);
             run<1, 4>("TMA bulk reduce add.f32, 128 B per op", red, cyc, threads, grid, 128);
             run<1, 8>("TMA bulk reduce add.f32, 128 B per op", red, cyc, threads, grid, 128);
             run<2, 4>("TMA bulk reduce add.f32, 256 B per op", red, cyc, threads, grid, 256);
+            run<3, 4>("REDG row + TMA 128-B row per iteration (2 rows)", red, cyc, threads, grid, 128);
         }
     }
     return 0;
