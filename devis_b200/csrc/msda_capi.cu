@@ -232,7 +232,7 @@ int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
     if (dtype != DEVIS_MSDA_F32 && dtype != DEVIS_MSDA_F64 && dtype != DEVIS_MSDA_BF16) return DEVIS_MSDA_ERR_BAD_DTYPE;
     if (outer < 0 || S < 0 || M <= 0 || D <= 0 || L <= 0 || Lq < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
     if (outer > 65535) return DEVIS_MSDA_ERR_TOO_LARGE;
-    // value rows are indexed with 31 bits (bit 31 carries a flag in the grouped kernels)
+    // value rows are indexed with 31-bit integers in every kernel
     if ((long long)outer * S >= (1LL << 31)) return DEVIS_MSDA_ERR_TOO_LARGE;
     return DEVIS_MSDA_OK;
 }
@@ -363,7 +363,6 @@ int devis_tmsda_forward(const void *value, const int64_t *spatial_shapes_host,
     int rc = check_common(num_frames, spatial_size, num_heads, channels, num_levels, num_query, dtype);
     if (rc) return rc;
     if (n_curr_points <= 0 || n_temporal_points < 0 || t_window < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
-    if (dtype == DEVIS_MSDA_F64 && false) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool temporal = t_window > 0 && n_temporal_points > 0;
     if (!spatial_shapes_host || !level_start_index_host || (temporal && !frame_table_host))
         return DEVIS_MSDA_ERR_NULL_POINTER;

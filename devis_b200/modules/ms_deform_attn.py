@@ -9,8 +9,9 @@
 
 What differs from the reference is only HOW the temporal modules evaluate a clip: the reference loops
 over the T frames in Python and issues two op calls and one gather copy of ``value`` per frame; here
-sampling locations for all frames are formed with a handful of broadcast ops and the whole clip is one
-``TemporalMSDeformAttnFunction`` call that reads ``value`` in place.
+the whole clip is one ``TemporalMSDeformAttnFunction`` call that reads ``value`` in place, and in the
+encoder (``fuse_prologue``) the kernels also take over the joint softmax and the location arithmetic
+(``TemporalMSDeformAttnFusedFunction``), reading the Linear outputs directly.
 """
 import math
 import warnings
@@ -191,14 +192,13 @@ class TemporalMSDeformAttnEncoder(TemporalMSDeformAttnBase):
             t, lq, _ = query.shape
             m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
             value = self.value_proj(input_flatten).view(t, input_flatten.shape[1], m, self.d_model // m)
-            if True:
-                out = TemporalMSDeformAttnFusedFunction.apply(
-                    value, reference_points,
-                    self.sampling_offsets(query).view(t, lq, m, nl, pc, 2),
-                    self.attention_weights(query).view(t, lq, m, nl * pc),
-                    self.temporal_sampling_offsets(query).view(t, lq, m, wt * nl, pt, 2),
-                    self.temporal_attention_weights(query).view(t, lq, m, wt * nl * pt), geom, order)
-                return self.output_proj(out), None
+            out = TemporalMSDeformAttnFusedFunction.apply(
+                value, reference_points,
+                self.sampling_offsets(query).view(t, lq, m, nl, pc, 2),
+                self.attention_weights(query).view(t, lq, m, nl * pc),
+                self.temporal_sampling_offsets(query).view(t, lq, m, wt * nl, pt, 2),
+                self.temporal_attention_weights(query).view(t, lq, m, wt * nl * pt), geom, order)
+            return self.output_proj(out), None
 
         value, off_c, off_t, aw_c, aw_t = self._compute_deformable_attention(query, input_flatten)
 
