@@ -149,6 +149,28 @@ def main():
     rc.fwd()
     res["ours_whole_clip"]["max_abs_diff_vs_ref_single_call"] = float((rc.out - want).abs().max())
     print("ours whole-clip", res["ours_whole_clip"], flush=True)
+    # decoder layer-clips (launch-bound regime): the reference's 12-call sequence vs ONE whole-clip launch
+    dec = {}
+    for lq in (10, 30, 300):
+        dclip = synthetic.make_clip(queries=lq, dist=a.dist, seed=2, device="cuda")
+        d_lc = [dclip["loc_curr"][t][None].contiguous() for t in range(T)]
+        d_ac = [dclip["aw_curr"][t][None].contiguous() for t in range(T)]
+        d_lt = [dclip["loc_temporal"][t][None].contiguous() for t in range(T)]
+        d_at = [dclip["aw_temporal"][t][None].contiguous() for t in range(T)]
+
+        def dec_seq_fwd(mod):
+            outs = []
+            for t in range(T):
+                cur = mod.ms_deform_attn_forward(dclip["value"][t][None], shapes, lsi, d_lc[t], d_ac[t], 64)
+                stacked = dclip["value"][idx[t]].flatten(0, 1)[None]
+                outs.append(cur + mod.ms_deform_attn_forward(stacked, tshapes, tlsi, d_lt[t], d_at[t], 64))
+            return torch.cat(outs, 0)
+
+        drc = RawClip(dclip, None)
+        dec[f"q{lq}"] = {"ref_sequence_fwd_us": med_us(lambda: dec_seq_fwd(ref), max(20, a.iters // 4), 5),
+                         "ours_whole_clip_fwd_us": med_us(drc.fwd, a.iters), "ours_whole_clip_bwd_us": med_us(drc.bwd, a.iters)}
+        print("decoder", lq, dec[f"q{lq}"], flush=True)
+    res["decoder_layer_clip"] = dec
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(res, fh, indent=1)

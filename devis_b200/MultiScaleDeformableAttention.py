@@ -85,8 +85,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step):
-    """vision.cpp:15 / ms_deform_attn.h:41-61.  Returns [grad_value, grad_sampling_loc, grad_attn_weight]."""
+                            im2col_step, need_grad_value=True):
+    """vision.cpp:15 / ms_deform_attn.h:41-61.  Returns [grad_value, grad_sampling_loc, grad_attn_weight].
+    ``need_grad_value=False`` (extension, used by the autograd Function when value is frozen) skips the scatter and
+    returns None in its place."""
     if not value.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
     _check([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
@@ -103,10 +105,11 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     shapes = spatial_shapes.to(torch.int64) if spatial_shapes.dtype != torch.int64 else spatial_shapes
     lsi = level_start_index.to(torch.int64) if level_start_index.dtype != torch.int64 else level_start_index
     acc_dtype = torch.float32 if value.dtype == torch.bfloat16 else value.dtype
-    grad_value = torch.empty(value.shape, dtype=acc_dtype, device=value.device)
+    grad_value = torch.empty(value.shape, dtype=acc_dtype, device=value.device) if need_grad_value else None
     grad_loc = torch.empty_like(loc)
     grad_aw = torch.empty_like(aw)
-    flags = _lib.FLAG_DETERMINISTIC if deterministic_enabled(value.dtype) else 0
+    flags = (_lib.FLAG_DETERMINISTIC if deterministic_enabled(value.dtype) else 0) | \
+        (0 if need_grad_value else _lib.FLAG_NO_GRAD_VALUE)
     lib = _lib.load()
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream
@@ -116,7 +119,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
             _ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(aw), _ptr(gout),
             _ptr(grad_value), _ptr(grad_loc), _ptr(grad_aw),
             n, s, m, d, nl, lq, p, max(int(im2col_step), 1), code, flags, _ptr(ws), ws_bytes, stream))
-    if grad_value.dtype != value.dtype:
+    if grad_value is not None and grad_value.dtype != value.dtype:
         grad_value = grad_value.to(value.dtype)
     if grad_loc.dtype != sampling_loc.dtype:
         grad_loc = grad_loc.to(sampling_loc.dtype)

@@ -9,6 +9,7 @@ derives it from the reference's module arguments with one device->host read that
 tensor (all 12 attention layers of a forward share the same tensors).
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -74,38 +75,63 @@ class ClipGeometry:
 
 
 # ------------------------------------------------------------------------------------------------
-_host_cache = {}
+# Host copies of the small integer tensors the reference passes around.  The copy is memoised ON THE TENSOR OBJECT
+# (attribute + version counter), never by address: a later forward with other image sizes allocates new tensors, and
+# the caching allocator may well hand them the same address again.
+# ------------------------------------------------------------------------------------------------
+_ATTR = "_devis_b200_host_copy"
 
 
 def _host_list(t):
-    """device int tensor -> nested python list, one synchronising read per (tensor storage, version)."""
+    """device int tensor -> nested python list; one synchronising read per tensor object and version."""
     if not isinstance(t, torch.Tensor):
         return [list(r) if hasattr(r, "__len__") else int(r) for r in t]
-    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
-    hit = _host_cache.get(key)
-    if hit is None:
-        if len(_host_cache) > 256:
-            _host_cache.clear()
-        hit = t.tolist()
-        _host_cache[key] = hit
-    return hit
+    hit = getattr(t, _ATTR, None)
+    if hit is not None and hit[0] == t._version:
+        return hit[1]
+    host = t.tolist()
+    try:
+        setattr(t, _ATTR, (t._version, host))
+    except AttributeError:      # exotic tensor subclasses without a __dict__: just do not memoise
+        pass
+    return host
+
+
+def _offsets_table(temporal_offsets):
+    """list of T per-frame offset tensors (or one (T, Wt) tensor) -> list of lists, with a single device read"""
+    if isinstance(temporal_offsets, torch.Tensor):
+        return _host_list(temporal_offsets)
+    tensors = [o for o in temporal_offsets if isinstance(o, torch.Tensor)]
+    if len(tensors) != len(temporal_offsets) or not tensors:
+        return [_host_list(o) for o in temporal_offsets]
+    first = tensors[0]
+    key = tuple((weakref.ref(o), o._version) for o in tensors)
+    hit = getattr(first, _ATTR + "_table", None)
+    if hit is not None and len(hit[0]) == len(key) and all(a[0]() is b[0]() and a[1] == b[1] for a, b in zip(hit[0], key)):
+        return hit[1]
+    if len({o.numel() for o in tensors}) == 1:
+        table = torch.stack([o.reshape(-1) for o in tensors]).tolist()      # one kernel, one read
+    else:
+        table = [o.tolist() for o in tensors]
+    try:
+        setattr(first, _ATTR + "_table", (key, table))
+    except AttributeError:
+        pass
+    return table
 
 
 _geom_cache = {}
 
 
 def from_reference_args(n_frames, input_spatial_shapes, input_level_start_index, temporal_offsets):
-    """Build (and memoise) the geometry from the arguments the reference modules receive
+    """Build (and memoise by VALUE) the geometry from the arguments the reference modules receive
     (ms_deform_attn.py:268-284): the (current, temporal) shape / start-index pairs and the list of
     per-frame temporal offset tensors."""
     cur_shapes = input_spatial_shapes[0] if isinstance(input_spatial_shapes, (tuple, list)) else input_spatial_shapes
     cur_lsi = input_level_start_index[0] if isinstance(input_level_start_index, (tuple, list)) else input_level_start_index
     shapes = tuple(tuple(r) for r in _host_list(cur_shapes))
     lsi = tuple(_host_list(cur_lsi))
-    if isinstance(temporal_offsets, torch.Tensor):
-        offs = _host_list(temporal_offsets)
-    else:
-        offs = [_host_list(o) for o in temporal_offsets]
+    offs = _offsets_table(temporal_offsets)
     table = tuple(tuple(int(o) + t for o in row) for t, row in enumerate(offs))
     key = (n_frames, shapes, lsi, table)
     geom = _geom_cache.get(key)

@@ -29,5 +29,6 @@ class MSDeformAttnFunction(Function):
     def backward(ctx, grad_output):
         value, shapes, lsi, loc, aw = ctx.saved_tensors
         grad_value, grad_loc, grad_aw = MSDA.ms_deform_attn_backward(
-            value, shapes, lsi, loc, aw, grad_output.contiguous(), ctx.im2col_step)
+            value, shapes, lsi, loc, aw, grad_output.contiguous(), ctx.im2col_step,
+            need_grad_value=ctx.needs_input_grad[0])
         return grad_value, None, None, grad_loc, grad_aw, None

@@ -117,3 +117,21 @@ def test_synthetic_workload_is_boundary_safe_and_sized_like_the_survey():
             assert frac.min() > 0.015 and frac.max() < 0.985
     fwd, bwd = synthetic.algorithmic_bytes(6, 4820, 8, 32, 4820, 96)
     assert (fwd, bwd) == (325754880, 621895680)          # 325.75 MB / 621.90 MB
+
+
+def test_host_copies_are_memoised_per_tensor_object_not_per_address():
+    """a tensor that re-uses a freed tensor's storage address with other values must not hit a stale cache"""
+    a = torch.tensor([[4, 6], [2, 3]])
+    lsi_a = torch.tensor([0, 24])
+    offs = [torch.tensor([1]), torch.tensor([-1])]
+    g1 = clip_geometry.from_reference_args(2, (a, None), (lsi_a, None), offs)
+    assert g1.shapes == [(4, 6), (2, 3)]
+    assert clip_geometry.from_reference_args(2, (a, None), (lsi_a, None), offs) is g1
+    a[0, 0] = 5                                            # in-place edit bumps the version -> re-read
+    lsi_b = torch.tensor([0, 30])
+    g2 = clip_geometry.from_reference_args(2, (a, None), (lsi_b, None), offs)
+    assert g2.shapes == [(5, 6), (2, 3)] and g2 is not g1
+    b = torch.tensor([[4, 6], [2, 3]])                     # new object, same values as the first call -> same geometry by value
+    assert clip_geometry.from_reference_args(2, (b, None), (lsi_a, None), [torch.tensor([1]), torch.tensor([-1])]) is g1
+    offs2 = [offs[0], torch.tensor([-1])]                  # same first tensor, different list -> table recomputed, equal value
+    assert clip_geometry.from_reference_args(2, (b, None), (lsi_a, None), offs2) is g1

@@ -200,3 +200,29 @@ def test_launches_are_counted_and_on_current_stream():
     side.synchronize()
     assert _lib.launch_count() == before + 1
     assert nmax(out.cpu().numpy(), g["out"]) < 1e-5
+
+
+def test_frozen_value_skips_grad_value():
+    from devis_b200 import MSDeformAttnFunction
+    g = load_golden("op_d32")
+    value, shapes, lsi, loc, aw, gout = _cuda(g, torch.float32)
+    l_, a = loc.clone().requires_grad_(True), aw.clone().requires_grad_(True)
+    out = MSDeformAttnFunction.apply(value, shapes, lsi, l_, a, 64)       # value does not require grad
+    out.backward(gout)
+    assert nmax(l_.grad.cpu().numpy(), g["gloc"]) < 1e-4 and nmax(a.grad.cpu().numpy(), g["gaw"]) < 1e-4
+
+
+def test_single_scale_long_clip_T36():
+    """the reference's single-scale T=36 ablation (docs/TRAIN.md:41): 1 level, 35 temporal frames, 2 temporal points"""
+    from devis_b200 import clip_geometry, synthetic, temporal_ms_deform_attn
+    from oracle import temporal_torch
+    shapes = ((12, 20),)
+    clip = synthetic.make_clip(n_frames=36, shapes=shapes, queries=5, pt=2, dist="uniform", seed=9, device="cuda")
+    geom = clip_geometry.ClipGeometry(shapes, 36, clip["frame_table"])
+    out = temporal_ms_deform_attn(clip["value"], clip["loc_curr"], clip["aw_curr"], clip["loc_temporal"],
+                                  clip["aw_temporal"], geom)
+    cpu = lambda k: clip[k].double().cpu()
+    offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(clip["frame_table"])]
+    ref = temporal_torch.temporal_core_per_frame(cpu("value"), cpu("loc_curr"), cpu("aw_curr"), cpu("loc_temporal"),
+                                                 cpu("aw_temporal"), torch.tensor(shapes), offs)
+    assert nmax(out.cpu().numpy(), ref.numpy()) < 1e-5
