@@ -69,3 +69,22 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src.replace("(/root/reference/", "("), f
+
+
+def test_missing_library_fails_loudly():
+    """no fallback: with the library absent every op raises (checked in a subprocess so this process keeps its library)"""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "import devis_b200\n"
+        "from devis_b200 import _lib\n"
+        "try:\n"
+        "    _lib.load()\n"
+        "    print('LOADED')\n"
+        "except _lib.MSDAError as e:\n"
+        "    print('RAISED', 'no CPU or PyTorch fallback' in str(e))\n" % ROOT)
+    env = dict(os.environ, DEVIS_MSDA_LIB="/nonexistent/libdevis_msda.so")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300).stdout
+    assert "RAISED True" in out, out

@@ -1,0 +1,101 @@
+"""Seeded shape fuzzing of the drop-in op against the C oracle (fp32) and the PyTorch oracle (fp64): random level
+pyramids, batch sizes, head / channel counts (grouped-lane kernels for D = 16, 32; generic kernels otherwise), point
+counts, query counts, with taps partly outside the maps.  Everything goes through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import nmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    nl = int(rng.integers(1, 6))
+    shapes = [(int(rng.integers(1, 14)), int(rng.integers(1, 18))) for _ in range(nl)]
+    n = int(rng.integers(1, 4))
+    m = int(rng.integers(1, 9))
+    d = int(rng.choice([32, 32, 16, 8, 24, 33, 64]))
+    lq = int(rng.integers(1, 70))
+    p = int(rng.integers(1, 6))
+    return shapes, n, m, d, lq, p
+
+
+def _inputs(seed, dtype):
+    from devis_b200 import synthetic
+    shapes, n, m, d, lq, p = _case(seed)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    s = sum(h * w for h, w in shapes)
+    sizes = torch.tensor([[w, h] for h, w in shapes], device="cuda", dtype=torch.float32)
+    loc = torch.rand(n, lq, m, len(shapes), p, 2, generator=g, device="cuda") * 1.5 - 0.25     # ~1/3 of taps off-map
+    loc = synthetic.make_boundary_safe(loc, sizes).to(dtype)
+    aw = torch.softmax(torch.randn(n, lq, m, len(shapes) * p, generator=g, device="cuda"), -1).view(n, lq, m, len(shapes), p).to(dtype)
+    value = torch.randn(n, s, m, d, generator=g, device="cuda").to(dtype)
+    gout = torch.randn(n, lq, m * d, generator=g, device="cuda").to(dtype)
+    shp = torch.tensor(shapes, device="cuda")
+    areas = shp[:, 0] * shp[:, 1]
+    lsi = torch.cat([areas.new_zeros(1), areas.cumsum(0)[:-1]])
+    return value, shp, lsi, loc.contiguous(), aw.contiguous(), gout
+
+
+def _run(value, shp, lsi, loc, aw, gout):
+    from devis_b200 import MSDeformAttnFunction
+    v, l_, a = (t.clone().requires_grad_(True) for t in (value, loc, aw))
+    out = MSDeformAttnFunction.apply(v, shp, lsi, l_, a, 64)
+    out.backward(gout)
+    return out.detach(), v.grad, l_.grad, a.grad
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_fuzz_fp32_vs_c_oracle(seed):
+    from oracle import c_oracle
+    args = _inputs(seed, torch.float32)
+    got = _run(*args)
+    value, shp, lsi, loc, aw, gout = (a.cpu().numpy() for a in args)
+    want = (c_oracle.forward(value, shp, lsi, loc, aw),) + c_oracle.backward(value, shp, lsi, loc, aw, gout)
+    for g, w, tol in zip(got, want, (1e-5, 1e-4, 1e-4, 1e-4)):
+        assert g.shape == w.shape
+        if np.abs(w).max() > 0:
+            assert nmax(g.cpu().numpy(), w) < tol, (_case(seed),)
+
+
+@pytest.mark.parametrize("seed", list(range(100, 108)))
+def test_fuzz_fp64_vs_pytorch_oracle(seed):
+    from oracle import msda_torch
+    args = _inputs(seed, torch.float64)
+    got = _run(*args)
+    value, shp, lsi, loc, aw, gout = (a.cpu() for a in args)
+    want = msda_torch.msda_forward_backward_torch(value, shp, loc, aw, gout)
+    for g, w in zip(got, want):
+        if w.abs().max() > 0:
+            assert nmax(g.cpu().numpy(), w.numpy()) < 1e-11, (_case(seed),)
+
+
+@pytest.mark.parametrize("seed", list(range(200, 206)))
+def test_fuzz_whole_clip_vs_per_call(seed):
+    """random clip geometries: the whole-clip op == sum of drop-in calls over (frame, slot) pairs"""
+    from devis_b200 import MSDeformAttnFunction, clip_geometry, synthetic, temporal_ms_deform_attn
+    rng = np.random.default_rng(seed)
+    t = int(rng.integers(2, 6))
+    shapes = tuple((int(rng.integers(2, 10)), int(rng.integers(2, 12))) for _ in range(int(rng.integers(1, 4))))
+    wt = int(rng.integers(1, t))
+    clip = synthetic.make_clip(n_frames=t, shapes=shapes, heads=int(rng.choice([2, 8])), channels=int(rng.choice([32, 16, 8])),
+                               pc=int(rng.integers(1, 5)), pt=int(rng.integers(1, 5)), queries=int(rng.integers(1, 40)),
+                               dist="uniform", seed=seed, device="cuda", t_window=wt)
+    table = [[int(rng.integers(0, t)) for _ in range(wt)] for _ in range(t)]       # arbitrary, duplicates allowed
+    geom = clip_geometry.ClipGeometry(shapes, t, table)
+    out = temporal_ms_deform_attn(clip["value"], clip["loc_curr"], clip["aw_curr"], clip["loc_temporal"],
+                                  clip["aw_temporal"], geom)
+    shp = torch.tensor(shapes, device="cuda")
+    areas = shp[:, 0] * shp[:, 1]
+    lsi = torch.cat([areas.new_zeros(1), areas.cumsum(0)[:-1]])
+    nl = len(shapes)
+    for f in range(t):
+        want = MSDeformAttnFunction.apply(clip["value"][f][None], shp, lsi, clip["loc_curr"][f][None].contiguous(),
+                                          clip["aw_curr"][f][None].contiguous(), 64)
+        for j, src in enumerate(table[f]):
+            want = want + MSDeformAttnFunction.apply(
+                clip["value"][src][None], shp, lsi, clip["loc_temporal"][f][None, :, :, j * nl:(j + 1) * nl].contiguous(),
+                clip["aw_temporal"][f][None, :, :, j * nl:(j + 1) * nl].contiguous(), 64)
+        assert nmax(out[f].cpu().numpy(), want[0].cpu().numpy()) < 2e-6
