@@ -102,6 +102,27 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
 #undef DEVIS_FWD8
         return check_launch();
     }
+    // 8 lanes x 4 channels with 16-byte tap records (msda_fwdc_kernel), D = 32 and P % 4 == 0: -4..5 % against the
+    // 32-byte records for fp32 value (default for fp32).  Tuning key 5: 1 always, 2 never.
+    const int compact_mode = g_tuning[5].load();
+    bool compact = lpg == 8 && (compact_mode == 1 || (compact_mode == 0 && dtype == DEVIS_MSDA_F32));
+    for (int sg = 0; sg < a.n_seg; ++sg) compact = compact && (a.seg[sg].P % 4 == 0);
+    if (compact) {
+        const LaunchShape s = pick_shape(d.Lq, 8, 0, 1);
+        smem += (size_t)(s.threads / 32) * Tap16x8::kBytesPerWarp;
+        const int qc = s.threads / 8;
+        const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
+        if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+        const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
+        if (dtype == DEVIS_MSDA_BF16) {
+            if (s.qpg == 2) msda_fwdc_kernel<true, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
+            else msda_fwdc_kernel<true, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
+        } else {
+            if (s.qpg == 2) msda_fwdc_kernel<false, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
+            else msda_fwdc_kernel<false, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
+        }
+        return check_launch();
+    }
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, lpg, 0, 1);
         smem += exchange_bytes(lpg, s.threads);
@@ -448,7 +469,8 @@ static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, co
     int rc = check_common(T, S, M, D, L, Lq, dtype);
     if (rc) return rc;
     if (Pc <= 0 || Pt < 0 || Wt < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
-    if (dtype == DEVIS_MSDA_F64 || D != 32) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    if (dtype == DEVIS_MSDA_F64 || D != 32 || Pc % 4 != 0 || (Wt > 0 && Pt > 0 && Pt % 4 != 0))
+        return DEVIS_MSDA_ERR_UNSUPPORTED;
     if ((unsigned long long)T * S * M * D * elem_size(dtype) >= (1ull << 32)) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool temporal = Wt > 0 && Pt > 0;
     if (!shapes || !lsi || (temporal && !frames)) return DEVIS_MSDA_ERR_NULL_POINTER;

@@ -153,6 +153,153 @@ __global__ void __launch_bounds__(256, DEVIS_FWD_MIN_BLOCKS) msda_fwd_kernel(con
 
 
 // =================================================================================================
+// msda_fwdc_kernel -- D = 32, EIGHT lanes per (query, head) like msda_fwd_kernel, but with the 16-byte tap
+// record of msda_fwd8_kernel (one LDS.128 per tap instead of two).  An exchange covers 8 taps = two aligned groups
+// of 4, each inside one slot (P % 4 == 0), so the two row pitches a consumer needs come from two shuffles per exchange.
+// =================================================================================================
+struct Tap16x8 {
+    static constexpr int kWordsPerWarpBuf = 8 * 4 * 4;  // 8 taps x 4 groups x 4 words
+    static constexpr int kBytesPerWarp = 2 * kWordsPerWarpBuf * 4;
+    // readers: fixed tap, 4 groups -> 4 consecutive 16-B records; writers (fixed group, 8 taps): 8 lanes of a
+    // quarter-warp write records 64 B apart -> swizzle the group slot with the tap index to spread the banks
+    __device__ static __forceinline__ int word(int j, int g) { return (j * 4 + (g ^ (j & 3))) * 4; }
+};
+
+
+// 16-byte tap record shared by msda_fwdc_kernel, msda_fwd8_kernel and the fused-prologue forward
+__device__ __forceinline__ uint4 make_tap16(const TapGeom &t, float w, unsigned rowbytes)
+{
+    uint4 rec;
+    rec.x = (unsigned)t.rTL * rowbytes | (unsigned)(t.rTR != t.rTL) | ((unsigned)(t.rBL != t.rTL) << 1) | (t.ok & 4u) |
+            (t.ok & 8u);
+    rec.y = __float_as_uint((t.ok & 1u) ? w * t.hh : 0.f);
+    rec.z = __float_as_uint((t.ok & 2u) ? w * t.lh : 0.f);
+    rec.w = __float_as_uint(t.lw);
+    return rec;
+}
+
+__device__ __forceinline__ void decode_tap16(const uint4 r, unsigned rowbytes, unsigned pitch, unsigned (&o)[4], float (&c)[4])
+{
+    const unsigned dcol = (r.x & 1u) ? rowbytes : 0u, drow = (r.x & 2u) ? pitch : 0u;
+    o[0] = r.x & ~15u;
+    o[1] = o[0] + dcol;
+    o[2] = o[0] + drow;
+    o[3] = o[2] + dcol;
+    const float lw = __uint_as_float(r.w);
+    const float hwm = (r.x & 4u) ? 1.f - lw : 0.f, lwm = (r.x & 8u) ? lw : 0.f;
+    const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
+    c[0] = whh * hwm;
+    c[1] = whh * lwm;
+    c[2] = wlh * hwm;
+    c[3] = wlh * lwm;
+}
+
+// one exchange of 8 published records -> 32 corner gathers and 128 FFMA per lane (8 lanes x 4 channels per row)
+template <bool BF16>
+__device__ __forceinline__ void consume_tap16x8(const float *buf, int g, unsigned rowbytes, unsigned pitch_lo,
+                                                unsigned pitch_hi, const char *vbase, float4 &acc)
+{
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += 2) {
+        unsigned o[2][4];
+        float c[2][4];
+        float4 v[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            decode_tap16(*reinterpret_cast<const uint4 *>(buf + Tap16x8::word(j0 + u, g)), rowbytes,
+                         (j0 + u) < 4 ? pitch_lo : pitch_hi, o[u], c[u]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                v[u][e] = BF16 ? ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + o[u][e]))
+                               : ldg_f4(reinterpret_cast<const float4 *>(vbase + o[u][e]));
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            acc.x = fmaf(c[u][3], v[u][3].x, fmaf(c[u][2], v[u][2].x, fmaf(c[u][1], v[u][1].x, fmaf(c[u][0], v[u][0].x, acc.x))));
+            acc.y = fmaf(c[u][3], v[u][3].y, fmaf(c[u][2], v[u][2].y, fmaf(c[u][1], v[u][1].y, fmaf(c[u][0], v[u][0].y, acc.y))));
+            acc.z = fmaf(c[u][3], v[u][3].z, fmaf(c[u][2], v[u][2].z, fmaf(c[u][1], v[u][1].z, fmaf(c[u][0], v[u][0].z, acc.z))));
+            acc.w = fmaf(c[u][3], v[u][3].w, fmaf(c[u][2], v[u][2].w, fmaf(c[u][1], v[u][1].w, fmaf(c[u][0], v[u][0].w, acc.w))));
+        }
+    }
+}
+
+template <bool BF16, int QPG, class SlotSrc>
+__global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc> a)
+{
+    constexpr int LPG = 8;
+    extern __shared__ int4 s_slot[];
+    const int outer = blockIdx.y;
+    build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16x8::kWordsPerWarpBuf);
+
+    const int M = a.d.M, Lq = a.d.Lq;
+    const int j = threadIdx.x & 7, g = (threadIdx.x & 31) >> 3, grp = threadIdx.x >> 3, QC = blockDim.x >> 3;
+    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+
+    int q[QPG];
+    bool qlive[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        const int qi = (qchunk * QPG + i) * QC + grp;
+        qlive[i] = qi < Lq;
+        q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
+    }
+
+    constexpr unsigned kQuadBytes = BF16 ? 8u : 16u;
+    const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
+    asm volatile("" : "+l"(vbase));
+
+    float4 acc[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int slot_base = 0, parity = 0;
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;   // P % 4 == 0, hence K % 4 == 0
+        const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
+        const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
+        for (int k0 = 0; k0 < K; k0 += LPG) {
+            const int k = k0 + j;
+            const bool klive = k < K;
+            const int4 sl = s_slot[slot_base + (klive ? k / P : 0)];
+            const unsigned my_pitch = (unsigned)sl.y * rowbytes;
+            const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);   // slot of taps k0 .. k0+3
+            const unsigned pitch_hi = __shfl_sync(0xffffffffu, my_pitch, 4, 8);   // slot of taps k0+4 .. k0+7
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) {
+                const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+                const bool live = klive && qlive[i];
+                float2 xy = make_float2(0.f, 0.f);
+                float w = 0.f;
+                if (live) {
+                    xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                    w = __ldg(aw + row * K + k);
+                }
+                const TapGeom t = tap_geometry(xy.x, xy.y, sl, live);
+                float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
+                parity ^= 1;
+                *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
+                __syncwarp();
+                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i]);
+            }
+        }
+        slot_base += a.seg[sg].n_slots;
+    }
+
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        if (!qlive[i]) continue;
+        const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+        if (BF16)
+            reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc[i]);
+        else
+            reinterpret_cast<float4 *>(a.out)[row * LPG + j] = acc[i];
+    }
+}
+
+// =================================================================================================
 // msda_fwd8_kernel -- D = 32 only: FOUR lanes per (query, head), 8 channels per lane.
 //
 // Round-1b profile + benchmarks/micro/l1_patterns.cu: the forward is bound by the SM's L1/shared data

@@ -17,6 +17,7 @@
 #pragma once
 #include "msda_bwd.cuh"
 #include "msda_common.cuh"
+#include "msda_fwd.cuh"
 
 namespace devis {
 
@@ -82,11 +83,10 @@ template <bool BF16>
 __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
-    using X = TapExchange<LPG>;
     extern __shared__ int4 s_slot[];
     const int outer = blockIdx.y, n_slots_total = a.n_slots[0] + (a.n_seg > 1 ? a.n_slots[1] : 0);
     build_slots(s_slot, a.src, a.d, outer, n_slots_total);
-    float *xbuf = reinterpret_cast<float *>(s_slot + n_slots_total) + (threadIdx.x >> 5) * (2 * X::kWordsPerWarpBuf);
+    float *xbuf = reinterpret_cast<float *>(s_slot + n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16x8::kWordsPerWarpBuf);
 
     const int M = a.d.M, Lq = a.d.Lq;
     const int j = threadIdx.x % LPG, g = (threadIdx.x & 31) / LPG, grp = threadIdx.x / LPG, QC = blockDim.x / LPG;
@@ -107,47 +107,23 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.P[sg], K = a.n_slots[sg] * P;
+        const int P = a.P[sg], K = a.n_slots[sg] * P;             // P % 4 == 0 (checked by the launcher)
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
             const bool live = k < K && qlive;
-            const int ls = live ? k / P : 0;                       // slot within the segment
+            const int ls = k < K ? k / P : 0;                      // slot within the segment
             const int4 sl = s_slot[slot_base + ls];
+            const unsigned my_pitch = (unsigned)sl.y * rowbytes;
+            const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);
+            const unsigned pitch_hi = __shfl_sync(0xffffffffu, my_pitch, 4, 8);
             float x = 0.f, y = 0.f, w = 0.f;
             if (live) fused_tap_operands(a, sg, row, qrow, k, K, sl, ls % a.src.L, rmax, rinv, x, y, w);
             const TapGeom t = tap_geometry(x, y, sl, live);
-            float *buf = xbuf + parity * X::kWordsPerWarpBuf;
+            float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
             parity ^= 1;
-            X::publish(buf, j, g, t, w, rowbytes);
+            *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
             __syncwarp();
-#pragma unroll
-            for (int j0 = 0; j0 < LPG; j0 += 2) {
-                uint4 off[2];
-                float4 c[2], v[2][4];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) X::fetch(buf, j0 + u, g, off[u], c[u]);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (BF16) {
-                        v[u][0] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].x));
-                        v[u][1] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].y));
-                        v[u][2] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].z));
-                        v[u][3] = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off[u].w));
-                    } else {
-                        v[u][0] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].x));
-                        v[u][1] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].y));
-                        v[u][2] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].z));
-                        v[u][3] = ldg_f4(reinterpret_cast<const float4 *>(vbase + off[u].w));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    acc.x = fmaf(c[u].w, v[u][3].x, fmaf(c[u].z, v[u][2].x, fmaf(c[u].y, v[u][1].x, fmaf(c[u].x, v[u][0].x, acc.x))));
-                    acc.y = fmaf(c[u].w, v[u][3].y, fmaf(c[u].z, v[u][2].y, fmaf(c[u].y, v[u][1].y, fmaf(c[u].x, v[u][0].y, acc.y))));
-                    acc.z = fmaf(c[u].w, v[u][3].z, fmaf(c[u].z, v[u][2].z, fmaf(c[u].y, v[u][1].z, fmaf(c[u].x, v[u][0].z, acc.z))));
-                    acc.w = fmaf(c[u].w, v[u][3].w, fmaf(c[u].z, v[u][2].w, fmaf(c[u].y, v[u][1].w, fmaf(c[u].x, v[u][0].w, acc.w))));
-                }
-            }
+            consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc);
         }
         slot_base += a.n_slots[sg];
     }

@@ -126,9 +126,10 @@ class TemporalMSDeformAttnFusedFunction(Function):
     (T,Lq,M,L,Pc,2); logit_curr (T,Lq,M,L*Pc); off_temporal (T,Lq,M,Wt*L,Pt,2); logit_temporal (T,Lq,M,Wt*L*Pt)."""
 
     @staticmethod
-    def supported(like, head_dim, reference_points):
+    def supported(like, head_dim, reference_points, n_curr_points=4, n_temporal_points=4):
         """`like`: a tensor with value's device, dtype and element count (e.g. the module's input_flatten)"""
         return (like.is_cuda and like.dtype in (torch.float32, torch.bfloat16) and head_dim == 32
+                and n_curr_points % 4 == 0 and n_temporal_points % 4 == 0
                 and reference_points.shape[-1] == 2 and like.numel() * like.element_size() < (1 << 32)
                 and not MSDA.deterministic_enabled(like.dtype))
 

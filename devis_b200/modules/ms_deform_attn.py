@@ -188,7 +188,8 @@ class TemporalMSDeformAttnEncoder(TemporalMSDeformAttnBase):
             order = geom.tile_order(query.device, *self.query_tile)
 
         if self.fuse_prologue and TemporalMSDeformAttnFusedFunction.supported(
-                input_flatten, self.d_model // self.n_heads, reference_points):
+                input_flatten, self.d_model // self.n_heads, reference_points, self.n_curr_points,
+                self.n_temporal_points):
             t, lq, _ = query.shape
             m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
             value = self.value_proj(input_flatten).view(t, input_flatten.shape[1], m, self.d_model // m)

@@ -67,7 +67,8 @@ uint64_t devis_msda_launch_count(void);
 /* Launch-shape knobs for benchmarking (process-wide; 0 restores the built-in heuristic).
  * key 0: forward threads per block, 1: forward queries per lane group,
  * key 2: backward threads per block, 3: backward queries per lane group,
- * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always (A/B testing). */
+ * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always (A/B testing),
+ * key 5: 8-lane forward kernel with 16-byte tap records: 0 = fp32 only (default), 1 = always, 2 = never. */
 int devis_msda_set_tuning(int key, int value);
 
 /*
@@ -153,7 +154,7 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
  *   logit_curr     (num_frames, num_query, num_heads, num_levels*n_curr_points) float           raw attention_weights output
  *   off_temporal   (num_frames, num_query, num_heads, t_window*num_levels, n_temporal_points, 2) float
  *   logit_temporal (num_frames, num_query, num_heads, t_window*num_levels*n_temporal_points) float
- * value / output / grad_output: DEVIS_MSDA_F32 or DEVIS_MSDA_BF16; channels must be 32 (else DEVIS_MSDA_ERR_UNSUPPORTED
+ * value / output / grad_output: DEVIS_MSDA_F32 or DEVIS_MSDA_BF16; channels must be 32 and the point counts multiples of 4 (else DEVIS_MSDA_ERR_UNSUPPORTED
  * and the caller uses devis_tmsda_forward on materialised operands).  The backward writes d/d(off_*) and d/d(logit_*)
  * directly; grad_value (float) is zero-filled by the call; flags: DEVIS_MSDA_FLAG_NO_GRAD_VALUE only.
  */
