@@ -52,7 +52,8 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.sm, self.reasons, self.power = [], set(), []
+        self.samples = []          # (perf_counter, sm MHz, reason mask, watts)
+        self.window = None         # (t0, t1): the timed region; samples outside it are dropped
         self.max_mhz = None
         self._stop = threading.Event()
         self.thread = None
@@ -77,24 +78,25 @@ class ClockSampler:
         nv = self.nv
         while not self._stop.is_set():
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                for name, bit in self.REASONS:
-                    if mask & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                watts = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((time.perf_counter(), mhz, mask, watts))
             except Exception as exc:  # noqa: BLE001
                 self.err = str(exc)
                 return
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop.set()
         if self.thread is not None:
             self.thread.join(timeout=1)
-        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
-               "samples": len(self.sm), "reasons": sorted(self.reasons),
-               "power_w_max": max(self.power) if self.power else None}
+        t0, t1 = self.window if self.window else (float("-inf"), float("inf"))
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        reasons = sorted({name for _, _, mask, _ in inside for name, bit in self.REASONS if mask & bit})
+        out = {"sm_mhz": statistics.median(x[1] for x in inside) if inside else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(inside), "reasons": reasons,
+               "power_w_max": max(x[3] for x in inside) if inside else None}
         if self.err:
             out["note"] = self.err
         return out
@@ -207,20 +209,22 @@ def run_ours(args, rank, world, local_rank):
             dist_mod.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()        # started before the warm-up so that NVML's slow first calls are over by the timed region
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.window = (t_region0, time.perf_counter())
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None

@@ -33,6 +33,7 @@ class RawClip:
         self.glt, self.gat = torch.empty_like(clip["loc_temporal"]), torch.empty_like(clip["aw_temporal"])
         self.order = order
         self.lib = _lib.load()
+        self.ws = None          # deterministic-mode workspace, allocated on first use
 
     def fwd(self):
         c, g = self.c, self.geom
@@ -44,12 +45,19 @@ class RawClip:
 
     def bwd(self, flags=0):
         c, g = self.c, self.geom
+        ws_ptr, ws_bytes = None, 0
+        if flags & _lib.FLAG_DETERMINISTIC:
+            ws_bytes = int(self.lib.devis_tmsda_backward_workspace_bytes(
+                self.t, self.s, self.m, self.d, g.n_levels, self.lq, self.pc, self.pt, g.t_window, self.code, flags))
+            if self.ws is None or self.ws.numel() < ws_bytes:
+                self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=c["value"].device)
+            ws_ptr = self.ws.data_ptr()
         _lib.check(self.lib.devis_tmsda_backward(
             ptr(c["value"]), g.shapes_ptr, g.lsi_ptr, g.frames_ptr, ptr(c["loc_curr"]), ptr(c["aw_curr"]),
             ptr(c["loc_temporal"]), ptr(c["aw_temporal"]), ptr(c["grad_out"]), ptr(self.gv), ptr(self.glc),
             ptr(self.gac), ptr(self.glt), ptr(self.gat), ptr(self.order),
             self.t, self.s, self.m, self.d, g.n_levels, self.lq, self.pc, self.pt, g.t_window, self.code, flags,
-            None, 0, torch.cuda.current_stream().cuda_stream))
+            ws_ptr, ws_bytes, torch.cuda.current_stream().cuda_stream))
 
 
 def time_us(fn, iters, warmup=5):
@@ -74,6 +82,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--sigma", type=float, default=2.0)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--det", action="store_true", help="also time the deterministic backward")
     a = ap.parse_args()
     dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype]
     clip = synthetic.make_clip(dist=a.dist, dtype=dtype, queries=a.queries or None, device="cuda", sigma_px=a.sigma)
@@ -99,6 +108,10 @@ def main():
             b2 = time_us(lambda: rc.bwd(2), a.iters)
             rows.append(dict(kind="bwd_nogv", order=oname, threads=threads, qpg=qpg, us=round(b2, 1)))
             print(rows[-1], flush=True)
+            if a.det:
+                b3 = time_us(lambda: rc.bwd(_lib.FLAG_DETERMINISTIC), max(3, a.iters // 4), warmup=2)
+                rows.append(dict(kind="bwd_det", order=oname, threads=threads, qpg=qpg, us=round(b3, 1)))
+                print(rows[-1], flush=True)
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(rows, fh, indent=1)

@@ -28,6 +28,10 @@
 #pragma once
 #include "msda_common.cuh"
 
+#ifndef DEVIS_BWD_MIN_BLOCKS
+#define DEVIS_BWD_MIN_BLOCKS 1
+#endif
+
 namespace devis {
 
 template <class SlotSrc>
@@ -67,7 +71,7 @@ __device__ __forceinline__ void reduce_scatter_taps(float (&d)[LPG][4], int j, f
 }
 
 template <bool BF16, int LPG, int QPG, class SlotSrc>
-__global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
+__global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
 {
     using X = TapExchange<LPG>;
     extern __shared__ int4 s_slot[];
@@ -107,8 +111,9 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
     // grad_value is always fp32: 16 bytes per channel quad; offsets published for `value` scale by 16/kQuadBytes
     char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * 16u : nullptr;
     constexpr unsigned kGvShift = BF16 ? 1u : 0u;
-    // deterministic mode: 8-byte fixed-point accumulators, same row layout -> offsets scale by 2 * 16 / kQuadBytes
-    char *detb = a.det.acc ? reinterpret_cast<char *>(a.det.acc) + (size_t)(m * LPG + j) * 32u : nullptr;
+    // deterministic mode: 8-byte fixed-point accumulators, same row pitch in elements -> offsets scale by
+    // 2 * 16 / kQuadBytes; within a (row, head) the channels are permuted (det_add4): lane j starts at word j
+    char *detb = a.det.acc ? reinterpret_cast<char *>(a.det.acc) + (size_t)(m * LPG) * 32u + (size_t)j * 8u : nullptr;
     const float det_sh = a.det.acc ? ldexpf(1.f, kDetFracBits - det_exponent(a.det.max_bits)) : 0.f;
 
     int slot_base = 0, parity = 0;
@@ -162,10 +167,10 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
                     dsum[jj][2] = fmaf(v10.w, gg.w, fmaf(v10.z, gg.z, fmaf(v10.y, gg.y, v10.x * gg.x)));
                     dsum[jj][3] = fmaf(v11.w, gg.w, fmaf(v11.z, gg.z, fmaf(v11.y, gg.y, v11.x * gg.x)));
                     if (detb) {
-                        if (c.x != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.x << (kGvShift + 1))), det_sh, c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
-                        if (c.y != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.y << (kGvShift + 1))), det_sh, c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
-                        if (c.z != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.z << (kGvShift + 1))), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
-                        if (c.w != 0.f) det_add4(reinterpret_cast<long long *>(detb + ((size_t)off.w << (kGvShift + 1))), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                        if (c.x != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.x << (kGvShift + 1))), det_sh, c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                        if (c.y != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.y << (kGvShift + 1))), det_sh, c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                        if (c.z != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.z << (kGvShift + 1))), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                        if (c.w != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.w << (kGvShift + 1))), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
                     } else if (gvb) {
                         if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
                         if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);

@@ -204,14 +204,14 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
             if (e != cudaSuccess) return cuda_fail(e);
         }
     }
+    const int lpg = lanes_per_group(dtype, d);
     auto finalize = [&]() -> int {
         if (!det || n_value == 0) return DEVIS_MSDA_OK;
-        det_finalize_kernel<<<148 * 8, 256, 0, st>>>(a.det.acc, final_grad_value, n_value, a.det.max_bits);
+        det_finalize_kernel<<<148 * 8, 256, 0, st>>>(a.det.acc, final_grad_value, n_value, a.det.max_bits, lpg);
         return check_launch();
     };
     if (d.outer == 0 || d.Lq == 0) return finalize();
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
-    const int lpg = lanes_per_group(dtype, d);
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, lpg, 2, 3);
         smem += exchange_bytes(lpg, s.threads);

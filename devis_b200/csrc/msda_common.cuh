@@ -222,13 +222,19 @@ __device__ __forceinline__ int det_exponent(const unsigned *max_bits)
     return e + 1;
 }
 
+// The grouped-lane kernels keep the accumulators of one (row, head) in a PERMUTED channel order: channel 4*j + c
+// (lane j's c-th channel) lives at element c*LPG + j, so that the LPG lanes of a group hit LPG consecutive 8-byte
+// words with each of their four reductions (64 contiguous bytes for LPG = 8; in channel order a lane's four words
+// are 32 bytes apart from its neighbour's and every 32-byte sector left the SM a quarter full: 9.7 ms per DeVIS
+// layer-clip backward).  det_finalize_kernel undoes the permutation.
+template <int LPG>
 __device__ __forceinline__ void det_add4(long long *p, float sh, float a, float b, float c, float d)
 {
     // sh is a power of two: the products below are exact; llrint of a float is exact as well
-    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 0, (unsigned long long)__float2ll_rn(a * sh));
-    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 1, (unsigned long long)__float2ll_rn(b * sh));
-    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 2, (unsigned long long)__float2ll_rn(c * sh));
-    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 3, (unsigned long long)__float2ll_rn(d * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 0 * LPG, (unsigned long long)__float2ll_rn(a * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 1 * LPG, (unsigned long long)__float2ll_rn(b * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 2 * LPG, (unsigned long long)__float2ll_rn(c * sh));
+    atomicAdd(reinterpret_cast<unsigned long long *>(p) + 3 * LPG, (unsigned long long)__float2ll_rn(d * sh));
 }
 
 // max|x| over n elements (float or bf16) into *slot, as the bits of a non-negative float (atomicMax on the
@@ -247,12 +253,19 @@ __global__ void __launch_bounds__(256) absmax_kernel(const void *x, size_t n, un
     if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
 }
 
+// lpg > 0: the accumulators of every D = 4*lpg channels are in the permuted order of det_add4; lpg == 0: channel order
 __global__ void __launch_bounds__(256) det_finalize_kernel(const long long *acc, float *out, size_t n,
-                                                           const unsigned *max_bits)
+                                                           const unsigned *max_bits, int lpg)
 {
     const double back = ldexp(1.0, det_exponent(max_bits) - kDetFracBits);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = (float)((double)acc[i] * back);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t src = i;
+        if (lpg) {
+            const int ch = (int)(i % (size_t)(4 * lpg));
+            src = i - ch + (size_t)((ch & 3) * lpg + (ch >> 2));
+        }
+        out[i] = (float)((double)acc[src] * back);
+    }
 }
 
 __device__ __forceinline__ uint2 pack_bf16x4(float4 v)
