@@ -28,8 +28,10 @@
 #pragma once
 #include "msda_common.cuh"
 
+// 3 blocks of 256 threads (6 of 128) per SM caps the kernel at 80 registers; uncapped, ptxas takes 84 - 115 and the
+// default 128-thread launch loses a block per SM (1428 -> 1440 us at 256 threads, equal at 128: sweep of round 1f)
 #ifndef DEVIS_BWD_MIN_BLOCKS
-#define DEVIS_BWD_MIN_BLOCKS 1
+#define DEVIS_BWD_MIN_BLOCKS 3
 #endif
 
 namespace devis {

@@ -55,18 +55,28 @@ struct LaunchShape {
     int threads, qpg;
 };
 
-LaunchShape pick_shape(int Lq, int lpg, int key_threads, int key_qpg)
+// Launch shape of the grouped-lane kernels.  Defaults from benchmarks/sweep.py at the DeVIS layer-clip shape
+// (profiles/r1f_sweep_*.json): the backward wants 128-thread blocks (84 registers -> 5 blocks = 20 warps per SM
+// against 2 x 8 warps with 256 threads: 1428 vs 1536 us), the fp32 forward 256 threads x 2 queries per group
+// (527 vs 549 us), the bf16 forward 128 threads.  Tuning keys override (developer tools only); max_qpg is the largest
+// QPG the chosen kernel is instantiated with -- anything else would launch a grid that does not cover the queries.
+enum ShapeKind { kShapeFwdF32, kShapeFwdBf16, kShapeBwd };
+
+LaunchShape pick_shape(int Lq, ShapeKind kind, int max_qpg, int key_threads, int key_qpg)
 {
     LaunchShape s;
     s.threads = g_tuning[key_threads].load();
     s.qpg = g_tuning[key_qpg].load();
-    if (s.threads == 0) s.threads = Lq >= 1024 ? 256 : Lq >= 128 ? 128 : 64;
-    if (s.qpg == 0) s.qpg = 1;
+    if (s.threads == 0) {
+        const int big = kind == kShapeFwdF32 ? 256 : 128;
+        s.threads = Lq >= 1024 ? big : Lq >= 128 ? 128 : 64;
+    }
+    if (s.qpg == 0) s.qpg = (kind == kShapeFwdF32 && Lq >= 2048) ? 2 : 1;
     if (s.threads < 32) s.threads = 32;
     if (s.threads > 256) s.threads = 256;
     s.threads = (s.threads / 32) * 32;
     if (s.qpg != 1 && s.qpg != 2 && s.qpg != 4) s.qpg = 1;
-    (void)lpg;
+    if (s.qpg > max_qpg) s.qpg = max_qpg;
     return s;
 }
 
@@ -85,7 +95,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     bool wide = lpg == 8 && (wide_mode == 2 || (wide_mode == 0 && dtype == DEVIS_MSDA_BF16));
     for (int sg = 0; sg < a.n_seg; ++sg) wide = wide && (a.seg[sg].P % 4 == 0);
     if (wide) {
-        const LaunchShape s = pick_shape(d.Lq, 4, 0, 1);
+        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 2, 0, 1);
         smem += (size_t)(s.threads / 32) * Tap16::kBytesPerWarp;
         const int qc = s.threads / 4;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -108,7 +118,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     bool compact = lpg == 8 && (compact_mode == 1 || (compact_mode == 0 && dtype == DEVIS_MSDA_F32));
     for (int sg = 0; sg < a.n_seg; ++sg) compact = compact && (a.seg[sg].P % 4 == 0);
     if (compact) {
-        const LaunchShape s = pick_shape(d.Lq, 8, 0, 1);
+        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 2, 0, 1);
         smem += (size_t)(s.threads / 32) * Tap16x8::kBytesPerWarp;
         const int qc = s.threads / 8;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -124,7 +134,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
         return check_launch();
     }
     if (lpg) {
-        const LaunchShape s = pick_shape(d.Lq, lpg, 0, 1);
+        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 4, 0, 1);
         smem += exchange_bytes(lpg, s.threads);
         const int qc = s.threads / lpg;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -213,7 +223,7 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
     if (d.outer == 0 || d.Lq == 0) return finalize();
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
     if (lpg) {
-        const LaunchShape s = pick_shape(d.Lq, lpg, 2, 3);
+        const LaunchShape s = pick_shape(d.Lq, kShapeBwd, 2, 2, 3);
         smem += exchange_bytes(lpg, s.threads);
         const int qc = s.threads / lpg;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -499,7 +509,7 @@ static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, co
 static int fused_grid(const FusedArgs &a, int key_threads, dim3 &grid, int &threads, size_t &smem)
 {
     threads = g_tuning[key_threads].load();
-    if (threads == 0) threads = a.d.Lq >= 1024 ? 256 : a.d.Lq >= 128 ? 128 : 64;
+    if (threads == 0) threads = a.d.Lq >= 1024 ? (key_threads == 2 ? 128 : 256) : a.d.Lq >= 128 ? 128 : 64;   // see pick_shape
     threads = threads < 32 ? 32 : threads > 256 ? 256 : (threads / 32) * 32;
     const long long chunks = ((long long)a.d.Lq + threads / 8 - 1) / (threads / 8);
     if (chunks * a.d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;

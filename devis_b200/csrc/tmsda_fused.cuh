@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256) tmsda_fused_bwd_kernel(const FusedArgs a)
+__global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
     using X = TapExchange<LPG>;
