@@ -57,7 +57,7 @@ def reference_style_encoder(mod, fn, query, ref, inp, shapes, lsi, tshapes, tlsi
     for t in range(query.shape[0]):
         loc = ref[t][None, :, None, :, None] + off_c[t][None] / norm[None, None, None, :, None, :]
         cur = fn(value[t][None], shapes, lsi, loc, aw_c[t][None], 64)
-        frames = offsets[t] + t
+        frames = offsets[t] + t if isinstance(offsets[t], torch.Tensor) else [o + t for o in offsets[t]]
         stacked = value[frames].flatten(0, 1)[None]
         tref = ref[t, :, 0][None, :, None, None, None]
         tloc = tref + off_t[t][None] / tnorm[None, None, None, :, None, :]

@@ -1,14 +1,18 @@
-"""Training-step benchmark of the DeVIS transformer trunk (BASELINE.json configs[4] without backbone / mask head /
-criterion, which are out of scope): 6 temporal-deformable encoder layers + 6 decoder layers on synthetic R50 T=6
-features, forward + backward + gradient all-reduce (DDP over NCCL, one clip per rank like main.py:85,131) +
-clip_grad_norm_(0.1) + AdamW -- the body of train_one_epoch (engine.py:48-77).
+"""Benchmarks of the DeVIS transformer trunk (devis_b200.DeVISTransformer: 6 temporal-deformable encoder layers + 6
+decoder layers) on synthetic R50 T=6 features -- BASELINE.json configs[2] and configs[4] without backbone / mask head /
+criterion, which are out of scope.
 
-    python benchmarks/train_step_bench.py [--steps 10] [--attn ours|reference]
+  --mode train   forward + backward + gradient all-reduce (DDP over NCCL, one clip per rank like main.py:85,131) +
+                 clip_grad_norm_(0.1) + AdamW: the body of train_one_epoch (engine.py:48-77)
+  --mode infer   eval-mode forward under no_grad (inference_vis, engine.py:207-232); --graph replays the whole trunk
+                 forward as ONE CUDA graph (possible because no layer reads a device tensor back: DeVISTransformer
+                 attaches host copies of the pyramid shape, devis_transformer.py prepare_data)
+
+    python benchmarks/train_step_bench.py [--mode train|infer] [--graph] [--steps 10] [--attn ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 benchmarks/train_step_bench.py
 
-The layer wrappers below restate deformable_transformer.py:143-173 (encoder layer) and :215-281 (decoder layer) as
-benchmark scaffolding; the attention modules are this repository's.  `--attn reference` swaps the temporal attention
-for the reference's per-frame loop around the reference's own CUDA op (oracle/_ref), single GPU only.
+`--attn reference` evaluates the encoder's temporal attention the reference's way -- per-frame loop, gather copies of
+value, the reference's own CUDA op (oracle/_ref) -- with the same parameters; single GPU only.
 """
 import argparse
 import json
@@ -21,8 +25,8 @@ import torch.distributed as dist
 from torch import nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from devis_b200 import synthetic  # noqa: E402
-from devis_b200.modules import TemporalMSDeformAttnDecoder, TemporalMSDeformAttnEncoder  # noqa: E402
+from devis_b200 import DeVISTransformer, synthetic  # noqa: E402
+from devis_b200.modules import TemporalMSDeformAttnEncoder  # noqa: E402
 
 
 class RefLoopEncoderAttn(TemporalMSDeformAttnEncoder):
@@ -36,62 +40,10 @@ class RefLoopEncoderAttn(TemporalMSDeformAttnEncoder):
                                        input_level_start_index[1], temporal_offsets), None
 
 
-class EncoderLayer(nn.Module):
-    def __init__(self, attn_cls, t, d=256, ffn=1024, drop=0.1):
-        super().__init__()
-        self.self_attn = attn_cls(t, d, 4, t - 1, 8, 4, 4)
-        self.drop1, self.norm1 = nn.Dropout(drop), nn.LayerNorm(d)
-        self.lin1, self.lin2 = nn.Linear(d, ffn), nn.Linear(ffn, d)
-        self.drop2, self.drop3, self.norm2 = nn.Dropout(drop), nn.Dropout(drop), nn.LayerNorm(d)
-
-    def forward(self, src, pos, ref, shapes, lsi, offsets):
-        a, _ = self.self_attn(src + pos, ref, src, shapes, lsi, offsets)
-        src = self.norm1(src + self.drop1(a))
-        f = self.lin2(self.drop2(torch.relu(self.lin1(src))))
-        return self.norm2(src + self.drop3(f))
-
-
-class DecoderLayer(nn.Module):
-    def __init__(self, t, d=256, ffn=1024, drop=0.1):
-        super().__init__()
-        self.cross_attn = TemporalMSDeformAttnDecoder(t, d, 4, t - 1, 8, 4, 4, True)
-        self.self_attn = nn.MultiheadAttention(d, 8, dropout=drop)
-        self.n1, self.n2, self.n3 = nn.LayerNorm(d), nn.LayerNorm(d), nn.LayerNorm(d)
-        self.d1, self.d2, self.d3, self.d4 = (nn.Dropout(drop) for _ in range(4))
-        self.lin1, self.lin2 = nn.Linear(d, ffn), nn.Linear(ffn, d)
-
-    def forward(self, tgt, qpos, ref, memory, shapes, lsi, offsets):
-        q = k = tgt + qpos
-        sa = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), tgt.transpose(0, 1))[0].transpose(0, 1)
-        tgt = self.n2(tgt + self.d2(sa))
-        ca = self.cross_attn(tgt + qpos, ref, memory, shapes, lsi, offsets)[0]
-        tgt = self.n1(tgt + self.d1(ca))
-        f = self.lin2(self.d3(torch.relu(self.lin1(tgt))))
-        return self.n3(tgt + self.d4(f))
-
-
-class Trunk(nn.Module):
-    def __init__(self, t, queries_per_frame, attn_cls, layers=6):
-        super().__init__()
-        self.enc = nn.ModuleList([EncoderLayer(attn_cls, t) for _ in range(layers)])
-        self.dec = nn.ModuleList([DecoderLayer(t) for _ in range(layers)])
-        self.query_embed = nn.Embedding(t * queries_per_frame, 512)
-        self.ref_proj = nn.Linear(256, 2)
-
-    def forward(self, src, pos, enc_ref, shapes, lsi, offsets):
-        mem = src
-        for layer in self.enc:
-            mem = layer(mem, pos, enc_ref, shapes, lsi, offsets)
-        qpos, tgt = torch.split(self.query_embed.weight, 256, dim=1)
-        qpos, tgt = qpos[None], tgt[None]
-        ref = self.ref_proj(qpos).sigmoid()[:, :, None].expand(-1, -1, 4, -1)      # (1, T*q, L, 2), valid ratio 1
-        for layer in self.dec:
-            tgt = layer(tgt, qpos, ref, mem, shapes, lsi, offsets)
-        return tgt, mem
-
-
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--graph", action="store_true", help="infer: replay the trunk forward as one CUDA graph")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--attn", default="ours", choices=["ours", "reference"])
@@ -103,37 +55,74 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    T, shapes_l, C = 6, synthetic.DEVIS_SHAPES, 256
+    torch.manual_seed(0)
+    # config.py defaults of every released DeVIS model: 4 current + 4 temporal points, all frames connected
+    trunk = DeVISTransformer(d_model=C, num_frames=T, enc_n_temporal_points=4, dec_n_temporal_points=4).to(dev)
+    query_embed = nn.Embedding(T * a.queries, 2 * C).to(dev)
     if a.attn == "reference":
         from benchmarks.module_bench import RefFunction
         from oracle import ref_cuda_build
         RefFunction.mod = ref_cuda_build.load()
         assert RefFunction.mod is not None and world == 1
-    T, shapes_l = 6, synthetic.DEVIS_SHAPES
-    S = sum(h * w for h, w in shapes_l)
-    torch.manual_seed(0)
-    model = Trunk(T, a.queries, TemporalMSDeformAttnEncoder if a.attn == "ours" else RefLoopEncoderAttn).to(dev)
+        for layer in trunk.encoder.layers:
+            layer.self_attn.__class__ = RefLoopEncoderAttn
+    model = nn.ModuleDict({"trunk": trunk, "query_embed": query_embed})
     n_params = sum(p.numel() for p in model.parameters())
-    if world > 1:
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=1e-4)
-    g = torch.Generator(device=dev).manual_seed(1 + rank)          # every rank its own clip
-    src = torch.randn(T, S, 256, device=dev, generator=g)
-    pos = torch.randn(T, S, 256, device=dev, generator=g)
-    enc_ref = synthetic.pixel_reference_points(shapes_l, T, dev)
-    shapes = torch.tensor(shapes_l, device=dev)
-    lsi = torch.tensor(synthetic.level_start_index(shapes_l), device=dev)
-    tshapes = shapes.repeat(T - 1, 1)
-    tlsi = torch.cat([tshapes.new_zeros(1), tshapes.prod(1).cumsum(0)[:-1]])
-    offsets = [torch.tensor([d for d in range(-t, T - t) if d != 0], device=dev) for t in range(T)]
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        tgt, mem = model(src, pos, enc_ref, (shapes, tshapes), (lsi, tlsi), offsets)
-        loss = tgt.square().mean() + 1e-3 * mem.square().mean()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
-        opt.step()
-        return loss
+    g = torch.Generator(device=dev).manual_seed(1 + rank)          # every rank its own clip
+    srcs = [torch.randn(T, C, h, w, device=dev, generator=g) for h, w in shapes_l]
+    pos = [torch.randn(T, C, h, w, device=dev, generator=g) for h, w in shapes_l]
+    masks = [torch.zeros(T, h, w, dtype=torch.bool, device=dev) for h, w in shapes_l]
+
+    class Step(nn.Module):                                         # one module so that DDP sees one forward
+        def __init__(self):
+            super().__init__()
+            self.m = model
+
+        def forward(self):
+            hs, _, memories, *_ = self.m["trunk"](srcs, masks, pos, self.m["query_embed"].weight)
+            return hs, memories
+
+    net = Step()
+    if a.mode == "train":
+        if world > 1:
+            net = nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
+        opt = torch.optim.AdamW(net.parameters(), lr=2e-4, weight_decay=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            hs, memories = net()
+            loss = hs[-1].square().mean() + 1e-3 * sum(m.square().mean() for m in memories)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 0.1)
+            opt.step()
+            return loss
+    else:
+        net.eval()
+        graph, static = None, {}
+
+        def eager():
+            with torch.no_grad():
+                hs, memories = net()
+            return hs[-1].square().mean()
+
+        if a.graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    eager()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static["loss"] = eager()
+
+        def step():
+            if graph is None:
+                return eager()
+            graph.replay()
+            return static["loss"]
 
     for _ in range(a.warmup):
         step()
@@ -154,10 +143,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:
-        res = {"workload": "DeVIS transformer trunk training step: 6 enc + 6 dec layers, T=6, S=4820, 10 queries/frame, "
-                           "fwd+bwd+grad all-reduce+clip+AdamW, fp32, synthetic features",
-               "attention": a.attn, "n_gpus": world, "ms_per_step": ms, "clips_per_sec": world / (ms * 1e-3),
-               "params": n_params, "grad_allreduce_bytes_per_step": n_params * 4 if world > 1 else 0,
+        what = ("training step: fwd+bwd+grad all-reduce+clip+AdamW" if a.mode == "train"
+                else "inference forward (eval, no_grad" + (", one CUDA graph)" if a.graph else ", eager)"))
+        res = {"workload": f"DeVIS transformer trunk {what}: 6 enc + 6 dec layers, T=6, S=4820, {a.queries} queries/frame, "
+                           "fp32, synthetic features",
+               "mode": a.mode, "cuda_graph": bool(a.graph), "attention": a.attn, "n_gpus": world, "ms_per_step": ms,
+               "clips_per_sec": world / (ms * 1e-3), "frames_per_sec": world * T / (ms * 1e-3), "params": n_params,
+               "grad_allreduce_bytes_per_step": n_params * 4 if (world > 1 and a.mode == "train") else 0,
                "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
         print(json.dumps(res), flush=True)
         if a.out:

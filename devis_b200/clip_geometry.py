@@ -55,6 +55,14 @@ class ClipGeometry:
         self._orders = {}
 
     # ------------------------------------------------------------------------------------------
+    def frame_table_tensor(self, device):
+        """(T, t_window) int64 frame indices on `device`, uploaded once (the decoder's instance-aware gather of
+        reference points indexes with it every layer; a fresh upload per call would also break CUDA-graph capture)"""
+        key = ("frames", str(device))
+        if key not in self._orders:
+            self._orders[key] = torch.as_tensor(self.frame_table, dtype=torch.long).reshape(self.n_frames, -1).to(device)
+        return self._orders[key]
+
     def tile_order(self, device, tile_h=8, tile_w=8):
         """Permutation of the S pixel-queries of one frame (encoder self-attention: query i is pixel i,
         deformable_transformer.py:184-198) that walks every level in tile_h x tile_w tiles.  Only
@@ -95,6 +103,41 @@ def _host_list(t):
     except AttributeError:      # exotic tensor subclasses without a __dict__: just do not memoise
         pass
     return host
+
+
+host_list = _host_list
+
+
+def attach_host_copy(t, host):
+    """Record the host value of a freshly built device tensor (shapes, start indices) so that `host_list` never has
+    to read it back: the producer knew the numbers before it uploaded them."""
+    try:
+        setattr(t, _ATTR, (t._version, host))
+    except AttributeError:
+        pass
+    return t
+
+
+_pyramid_cache = {}
+
+
+def pyramid_tensors(shapes, device):
+    """(spatial_shapes (L,2), level_start_index (L,)) int64 device tensors for a pyramid given as host numbers, with
+    their host copies attached; uploaded once per (shapes, device) and reused by every later forward."""
+    shapes = tuple((int(h), int(w)) for h, w in shapes)
+    key = (shapes, str(device))
+    hit = _pyramid_cache.get(key)
+    if hit is None:
+        if len(_pyramid_cache) > 64:
+            _pyramid_cache.clear()
+        starts, acc = [], 0
+        for h, w in shapes:
+            starts.append(acc)
+            acc += h * w
+        hit = (attach_host_copy(torch.as_tensor(shapes, dtype=torch.long).to(device), [list(s) for s in shapes]),
+               attach_host_copy(torch.as_tensor(starts, dtype=torch.long).to(device), starts))
+        _pyramid_cache[key] = hit
+    return hit
 
 
 def _offsets_table(temporal_offsets):

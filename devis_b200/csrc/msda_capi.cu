@@ -118,7 +118,8 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     bool compact = lpg == 8 && (compact_mode == 1 || (compact_mode == 0 && dtype == DEVIS_MSDA_F32));
     for (int sg = 0; sg < a.n_seg; ++sg) compact = compact && (a.seg[sg].P % 4 == 0);
     if (compact) {
-        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 2, 0, 1);
+        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32,
+                                         dtype == DEVIS_MSDA_BF16 ? 2 : 4, 0, 1);
         smem += (size_t)(s.threads / 32) * Tap16x8::kBytesPerWarp;
         const int qc = s.threads / 8;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -128,7 +129,8 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
             if (s.qpg == 2) msda_fwdc_kernel<true, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
             else msda_fwdc_kernel<true, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
         } else {
-            if (s.qpg == 2) msda_fwdc_kernel<false, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
+            if (s.qpg == 4) msda_fwdc_kernel<false, 4, SlotSrc><<<grid, s.threads, smem, st>>>(a);
+            else if (s.qpg == 2) msda_fwdc_kernel<false, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
             else msda_fwdc_kernel<false, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
         }
         return check_launch();

@@ -237,7 +237,7 @@ class TemporalMSDeformAttnDecoder(TemporalMSDeformAttnBase):
         # reference point each temporal (slot, level) starts from: the same query's own reference in the
         # sampled frame when instance-aware (:342-344), else its frame-t reference repeated (:346-347)
         if self.dec_instance_aware_att:
-            table = torch.as_tensor(geom.frame_table, device=query.device, dtype=torch.long)   # (T, Wt)
+            table = geom.frame_table_tensor(query.device)                                      # (T, Wt)
             ref_t = reference_points[table].permute(0, 2, 1, 3, 4).flatten(2, 3)                 # (T,q,Wt*L,.)
         else:
             ref_t = reference_points.repeat(1, 1, self.t_window, 1)

@@ -13,6 +13,9 @@ reference's own Python code executed here:
               float64, including their state_dict
   book_*.npz  the temporal bookkeeping tensors DeVISTransformerEncoder/Decoder hand to
               their layers (devis_transformer.py:90-123,140-173)
+  trunk_*.npz the reference DeVISTransformer (devis_transformer.py:17-75: prepare_data, 2 temporal encoder
+              layers, 2 temporal decoder layers with iterative box refinement) on a small padded clip:
+              every output of its forward, input gradients and all parameter gradients, float64
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -309,9 +312,68 @@ def make_module_fixtures(mods, devis_tr, def_tr):
     torch.set_default_dtype(torch.float32)
 
 
+# --------------------------------------------------------------------------------------
+# trunk-level fixtures: the callers of the attention modules
+# --------------------------------------------------------------------------------------
+def make_trunk_fixtures(devis_tr):
+    torch.set_default_dtype(torch.float64)
+    gen = torch.Generator().manual_seed(4242)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=gen, dtype=torch.float64)
+
+    c, heads, nl, t_frames, q, ffn = 32, 4, 2, 3, 5, 64
+    level_hw = [(6, 8), (3, 4)]
+    for tag, connect_all, window in (("all", True, 2), ("window", False, 2)):
+        tr = devis_tr.DeVISTransformer(d_model=c, num_frames=t_frames, nhead=heads, num_encoder_layers=2,
+                                       num_decoder_layers=2, dim_feedforward=ffn, dropout=0.0, num_feature_levels=nl,
+                                       enc_connect_all_embeddings=connect_all, enc_temporal_window=window,
+                                       enc_n_curr_points=2, enc_n_temporal_points=2, dec_n_curr_points=2,
+                                       dec_n_temporal_points=2, dec_instance_aware_att=True, with_gradient=False).double()
+        # iterative box refinement as DeformableDETR installs it (deformable_detr.py: decoder.bbox_embed = ModuleList)
+        tr.decoder.bbox_embed = torch.nn.ModuleList(
+            [torch.nn.Sequential(torch.nn.Linear(c, c), torch.nn.ReLU(), torch.nn.Linear(c, 4)) for _ in range(2)]).double()
+        randomize(tr, gen)
+        srcs = [rnd(t_frames, c, h, w) for h, w in level_hw]
+        pos = [rnd(t_frames, c, h, w) for h, w in level_hw]
+        masks = []
+        for h, w in level_hw:                      # right / bottom padding, different per frame
+            m = torch.zeros(t_frames, h, w, dtype=torch.bool)
+            for t in range(t_frames):
+                m[t, h - (t % 2):, :] = True
+                m[t, :, w - t:] = True
+            masks.append(m)
+        query_embed = rnd(t_frames * q, 2 * c)
+        leaves = [x.clone().requires_grad_(True) for x in srcs] + [query_embed.clone().requires_grad_(True)]
+        hs, qe, memories, init_ref, inter_refs, lsi, valid, shapes = tr(leaves[:nl], masks, pos, leaves[nl])
+        g_hs = rnd(*hs.shape)
+        g_mem = [rnd(*m.shape) for m in memories]
+        loss = (hs * g_hs).sum() + sum((m * g).sum() for m, g in zip(memories, g_mem))
+        params = dict(tr.named_parameters())
+        grads = torch.autograd.grad(loss, leaves + list(params.values()), allow_unused=True)
+        arrays = {f"src{i}": srcs[i] for i in range(nl)}
+        arrays.update({f"pos{i}": pos[i] for i in range(nl)})
+        arrays.update({f"mask{i}": masks[i] for i in range(nl)})
+        arrays.update({f"memory{i}": memories[i] for i in range(nl)})
+        arrays.update({f"g_memory{i}": g_mem[i] for i in range(nl)})
+        arrays.update({f"g_src{i}": grads[i] for i in range(nl)})
+        # parameter gradients: the attention modules', the level embedding's and the reference-point head's
+        arrays.update({"pg." + k: (g if g is not None else torch.zeros_like(prm))
+                       for (k, prm), g in zip(params.items(), grads[nl + 1:])
+                       if "_attn." in k and "layers.0." in k and "self_attn.in_proj" not in k and "out_proj" not in k
+                       or k.startswith(("level_embed", "reference_points"))})
+        save(f"trunk_{tag}", query_embed=query_embed, hs=hs, g_hs=g_hs, init_ref=init_ref, inter_refs=inter_refs,
+             lsi=lsi, valid_ratios=valid, shapes=shapes, g_query_embed=grads[nl],
+             cfg=np.array([c, t_frames, heads, 2, 2, ffn, nl, int(connect_all), window, 2, 2, q]),
+             **arrays, **sd_arrays(tr))
+    torch.set_default_dtype(torch.float32)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("the reference is not mounted; fixtures can only be regenerated in the build container")
     func_mod, mods_mod, devis_tr_mod, def_tr_mod = import_reference()
-    make_op_fixtures(func_mod)
-    make_module_fixtures(mods_mod, devis_tr_mod, def_tr_mod)
+    if "--only-trunk" not in sys.argv:
+        make_op_fixtures(func_mod)
+        make_module_fixtures(mods_mod, devis_tr_mod, def_tr_mod)
+    make_trunk_fixtures(devis_tr_mod)

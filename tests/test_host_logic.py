@@ -135,3 +135,71 @@ def test_host_copies_are_memoised_per_tensor_object_not_per_address():
     assert clip_geometry.from_reference_args(2, (b, None), (lsi_a, None), [torch.tensor([1]), torch.tensor([-1])]) is g1
     offs2 = [offs[0], torch.tensor([-1])]                  # same first tensor, different list -> table recomputed, equal value
     assert clip_geometry.from_reference_args(2, (b, None), (lsi_a, None), offs2) is g1
+
+
+def _trunk_from_fixture(g, dtype=torch.float64):
+    from devis_b200 import DeVISTransformer
+    c, t_frames, heads, n_enc, n_dec, ffn, nl, connect_all, window, pc, pt, _ = [int(x) for x in g["cfg"]]
+    tr = DeVISTransformer(d_model=c, num_frames=t_frames, nhead=heads, num_encoder_layers=n_enc,
+                          num_decoder_layers=n_dec, dim_feedforward=ffn, dropout=0.0, num_feature_levels=nl,
+                          enc_connect_all_embeddings=bool(connect_all), enc_temporal_window=window,
+                          enc_n_curr_points=pc, enc_n_temporal_points=pt, dec_n_curr_points=pc, dec_n_temporal_points=pt)
+    tr.decoder.bbox_embed = torch.nn.ModuleList(
+        [torch.nn.Sequential(torch.nn.Linear(c, c), torch.nn.ReLU(), torch.nn.Linear(c, 4)) for _ in range(n_dec)])
+    return tr.to(dtype)
+
+
+@pytest.mark.parametrize("tag", ["all", "window"])
+def test_transformer_mirror_has_reference_state_dict_and_bookkeeping(tag):
+    """parameter names / shapes of DeVISTransformer are the reference's (checkpoints load), and the host-side parts of
+    its forward -- prepare_data, valid ratios, encoder reference points, frame offsets -- reproduce the reference's"""
+    g = load_golden(f"trunk_{tag}")
+    tr = _trunk_from_fixture(g)
+    want = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    have = tr.state_dict()
+    assert set(want) == set(have)
+    assert all(tuple(have[k].shape) == want[k].shape for k in want)
+    tr.load_state_dict({k: torch.from_numpy(v) for k, v in want.items()})
+
+    nl = int(g["cfg"][6])
+    srcs = [torch.from_numpy(g[f"src{i}"]) for i in range(nl)]
+    masks = [torch.from_numpy(g[f"mask{i}"]) for i in range(nl)]
+    pos = [torch.from_numpy(g[f"pos{i}"]) for i in range(nl)]
+    src, mask, pos_flat, shapes, lsi, valid = tr.prepare_data(srcs, masks, pos)
+    assert np.array_equal(shapes.numpy(), g["shapes"]) and np.array_equal(lsi.numpy(), g["lsi"])
+    assert np.abs(valid.numpy() - g["valid_ratios"]).max() < 1e-12
+    assert clip_geometry.host_list(shapes) == g["shapes"].tolist()          # attached host copy, no device read
+    assert src.shape == (srcs[0].shape[0], int(g["shapes"].prod(1).sum()), srcs[0].shape[1]) and mask.shape == src.shape[:2]
+    level0 = pos[0].flatten(2).transpose(1, 2) + tr.level_embed[0].view(1, 1, -1)
+    assert torch.equal(pos_flat[:, :level0.shape[1]], level0)
+
+    # encoder reference points and frame offsets against the reference encoder's (book_enc_* fixtures)
+    book = load_golden(f"book_enc_{tag}")
+    ref = tr.encoder.get_reference_points(torch.from_numpy(book["shapes"]), torch.from_numpy(book["valid_ratios"]), "cpu")
+    assert np.abs(ref.numpy() - book["ref"]).max() < 1e-6                    # linspace is float32 in the reference too
+    tr.encoder.t_window = int(book["t_window"])
+    assert tr.encoder.frame_offsets(book["temporal_offsets"].shape[0]) == book["temporal_offsets"].tolist()
+
+
+def test_decoder_mirror_scales_reference_points_like_the_reference():
+    """2-d points and 4-d boxes are scaled by FRAME 0's valid ratios for every frame (devis_transformer.py:161-166)"""
+    from devis_b200 import DeVISTransformerDecoder
+    for tag in ("2d", "4d"):
+        g = load_golden(f"book_dec_{tag}")
+        seen = {}
+
+        class Capture(torch.nn.Module):
+            def forward(self, output, query_pos, ref_in, src, shapes_pair, lsi_pair, temporal_offsets):
+                seen.update(ref_in=ref_in, tshapes=shapes_pair[1], tlsi=lsi_pair[1], offsets=temporal_offsets)
+                return output
+
+        dec = DeVISTransformerDecoder(Capture(), 1)
+        ref = torch.from_numpy(g["ref"])
+        t_frames = g["valid_ratios"].shape[0]
+        s = int(g["shapes"].prod(1).sum())
+        hs, refs = dec(torch.zeros(1, ref.shape[1], 8, dtype=torch.float64), ref, torch.zeros(t_frames, s, 8, dtype=torch.float64),
+                       torch.from_numpy(g["shapes"]), torch.from_numpy(g["lsi"]), torch.from_numpy(g["valid_ratios"]))
+        assert np.abs(seen["ref_in"].numpy() - g["ref_in"]).max() < 1e-15
+        assert np.array_equal(seen["tshapes"].numpy(), g["tshapes"]) and np.array_equal(seen["tlsi"].numpy(), g["tlsi"])
+        assert seen["offsets"] == g["temporal_offsets"].tolist()
+        assert hs.shape[0] == 1 and torch.equal(refs[0], ref)
