@@ -190,6 +190,11 @@ def run_ours(args, rank, world, local_rank):
         dist_mod.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+    half_acc = args.bf16_accumulate and dtype == torch.bfloat16
+    if half_acc:
+        from devis_b200 import MultiScaleDeformableAttention as MSDA
+        MSDA.set_bf16_grad_value_accumulation(True)
+    bwd_flags = _lib.FLAG_BF16_GRAD_VALUE if half_acc else 0
     clip = synthetic.make_clip(dist=args.dist, dtype=dtype, seed=100 + rank, device=dev)
     geom = clip_geometry.ClipGeometry(clip["shapes"], T_FRAMES, clip["frame_table"])
     order = geom.tile_order(dev, 8, 8)
@@ -244,11 +249,11 @@ def run_ours(args, rank, world, local_rank):
     f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     b_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for _ in range(3):
-        raw.fwd(); raw.bwd()
+        raw.fwd(); raw.bwd(bwd_flags)
     torch.cuda.synchronize()
     for (fa, fb), (ba, bb) in zip(f_ev, b_ev):
         fa.record(); raw.fwd(); fb.record()
-        ba.record(); raw.bwd(); bb.record()
+        ba.record(); raw.bwd(bwd_flags); bb.record()
     torch.cuda.synchronize()
     us_fwd = statistics.mean(a.elapsed_time(b) for a, b in f_ev) * 1e3
     us_bwd = statistics.mean(a.elapsed_time(b) for a, b in b_ev) * 1e3
@@ -325,7 +330,8 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "dist": args.dist, "taps": "boundary-safe",
                        "l2_policy": "inputs larger than L2 (326 MB of operands per step vs 126 MB L2); no flush",
-                       "clips_per_rank_per_step": 1, "parallelism": f"clip-sharded x{world}, no collective"},
+                       "clips_per_rank_per_step": 1, "parallelism": f"clip-sharded x{world}, no collective",
+                       "grad_value_accumulation": "bf16 (opt-in flag)" if half_acc else "f32"},
             "us_fwd": us_fwd, "us_bwd": us_bwd,
             "roofline": {"bound": "hbm", "kernel": "msda_bwd_kernel", "achieved": bytes_b / us_bwd / 1e3, "peak": peak,
                          "unit": "GB/s", "frac": bytes_b / us_bwd / 1e3 / peak, "traffic": ncu_traffic("msda_bwd_kernel"),
@@ -360,6 +366,8 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--dist", default="local", choices=["local", "uniform"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bf16-accumulate", action="store_true",
+                    help="with --dtype bf16: accumulate grad_value in bf16 (DEVIS_MSDA_FLAG_BF16_GRAD_VALUE, opt-in)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

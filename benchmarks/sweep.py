@@ -29,6 +29,7 @@ class RawClip:
         self.code = {torch.float32: 0, torch.float64: 1, torch.bfloat16: 2}[v.dtype]
         self.out = torch.empty(self.t, self.lq, self.m * self.d, dtype=v.dtype, device=v.device)
         self.gv = torch.empty(v.shape, dtype=torch.float32, device=v.device)
+        self.gv_half = torch.empty(v.shape, dtype=torch.bfloat16, device=v.device) if v.dtype == torch.bfloat16 else None
         self.glc, self.gac = torch.empty_like(clip["loc_curr"]), torch.empty_like(clip["aw_curr"])
         self.glt, self.gat = torch.empty_like(clip["loc_temporal"]), torch.empty_like(clip["aw_temporal"])
         self.order = order
@@ -54,7 +55,8 @@ class RawClip:
             ws_ptr = self.ws.data_ptr()
         _lib.check(self.lib.devis_tmsda_backward(
             ptr(c["value"]), g.shapes_ptr, g.lsi_ptr, g.frames_ptr, ptr(c["loc_curr"]), ptr(c["aw_curr"]),
-            ptr(c["loc_temporal"]), ptr(c["aw_temporal"]), ptr(c["grad_out"]), ptr(self.gv), ptr(self.glc),
+            ptr(c["loc_temporal"]), ptr(c["aw_temporal"]), ptr(c["grad_out"]),
+            ptr(self.gv_half if flags & _lib.FLAG_BF16_GRAD_VALUE else self.gv), ptr(self.glc),
             ptr(self.gac), ptr(self.glt), ptr(self.gat), ptr(self.order),
             self.t, self.s, self.m, self.d, g.n_levels, self.lq, self.pc, self.pt, g.t_window, self.code, flags,
             ws_ptr, ws_bytes, torch.cuda.current_stream().cuda_stream))
@@ -108,6 +110,10 @@ def main():
             b2 = time_us(lambda: rc.bwd(2), a.iters)
             rows.append(dict(kind="bwd_nogv", order=oname, threads=threads, qpg=qpg, us=round(b2, 1)))
             print(rows[-1], flush=True)
+            if a.dtype == "bf16":
+                b4 = time_us(lambda: rc.bwd(_lib.FLAG_BF16_GRAD_VALUE), a.iters)
+                rows.append(dict(kind="bwd_bf16acc", order=oname, threads=threads, qpg=1, us=round(b4, 1)))
+                print(rows[-1], flush=True)
             if a.det:
                 b3 = time_us(lambda: rc.bwd(_lib.FLAG_DETERMINISTIC), max(3, a.iters // 4), warmup=2)
                 rows.append(dict(kind="bwd_det", order=oname, threads=threads, qpg=qpg, us=round(b3, 1)))

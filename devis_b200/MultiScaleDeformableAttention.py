@@ -30,6 +30,25 @@ def deterministic_enabled(value_dtype=None):
     return on and value_dtype != torch.float64      # fp64 keeps native double atomics (gradcheck path)
 
 
+# process-wide switch for the bf16 grad_value accumulation; see set_bf16_grad_value_accumulation()
+_bf16_accumulate = False
+
+
+def set_bf16_grad_value_accumulation(flag):
+    """bf16 value only.  False (default): grad_value is accumulated in float32 and rounded to bf16 once.  True: the
+    scatter adds straight into a bf16 grad_value with packed bf16 reductions (DEVIS_MSDA_FLAG_BF16_GRAD_VALUE) --
+    half the bytes leave the SM, which is what bounds the backward, at the precision of PyTorch's own bf16
+    atomicAdd scatters (every partial sum rounds to bf16).  Ignored in deterministic mode and for head dims other
+    than 16 / 32."""
+    global _bf16_accumulate
+    _bf16_accumulate = bool(flag)
+
+
+def bf16_accumulate_enabled(value):
+    return (_bf16_accumulate and value.dtype == torch.bfloat16 and value.shape[-1] in (16, 32)
+            and value.numel() * 2 < (1 << 32) and not deterministic_enabled(value.dtype))
+
+
 def _check(named, like=None):
     for name, t in named:
         if not t.is_contiguous():
@@ -104,12 +123,13 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     gout = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
     shapes = spatial_shapes.to(torch.int64) if spatial_shapes.dtype != torch.int64 else spatial_shapes
     lsi = level_start_index.to(torch.int64) if level_start_index.dtype != torch.int64 else level_start_index
-    acc_dtype = torch.float32 if value.dtype == torch.bfloat16 else value.dtype
+    half_acc = need_grad_value and bf16_accumulate_enabled(value)
+    acc_dtype = torch.float32 if (value.dtype == torch.bfloat16 and not half_acc) else value.dtype
     grad_value = torch.empty(value.shape, dtype=acc_dtype, device=value.device) if need_grad_value else None
     grad_loc = torch.empty_like(loc)
     grad_aw = torch.empty_like(aw)
     flags = (_lib.FLAG_DETERMINISTIC if deterministic_enabled(value.dtype) else 0) | \
-        (0 if need_grad_value else _lib.FLAG_NO_GRAD_VALUE)
+        (0 if need_grad_value else _lib.FLAG_NO_GRAD_VALUE) | (_lib.FLAG_BF16_GRAD_VALUE if half_acc else 0)
     lib = _lib.load()
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DEVIS_MSDA_LIB") or os.path.join(_HERE, "libdevis_msd
 
 ABI_VERSION = 1
 F32, F64, BF16 = 0, 1, 2
-FLAG_DETERMINISTIC, FLAG_NO_GRAD_VALUE = 1, 2
+FLAG_DETERMINISTIC, FLAG_NO_GRAD_VALUE, FLAG_BF16_GRAD_VALUE = 1, 2, 4
 
 _vp, _i, _u, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
 

@@ -40,7 +40,7 @@ template <class SlotSrc>
 struct BwdArgs {
     const void *value;
     const void *grad_out;
-    float *grad_value;  // fp32 accumulation target (also for bf16 value); nullptr = skip
+    void *grad_value;   // fp32 accumulation target (also for bf16 value; bf16 under HALF_ACC); nullptr = skip
     DetScale det;       // deterministic mode: det.acc != nullptr replaces the float reductions
     Segment seg[2];
     int n_seg;
@@ -72,7 +72,10 @@ __device__ __forceinline__ void reduce_scatter_taps(float (&d)[LPG][4], int j, f
     for (int c = 0; c < 4; ++c) r[c] = d[0][c];
 }
 
-template <bool BF16, int LPG, int QPG, class SlotSrc>
+// HALF_ACC (bf16 value only, DEVIS_MSDA_FLAG_BF16_GRAD_VALUE): grad_value is a bf16 tensor laid out like value and
+// the scatter uses 8-byte packed reductions (red.global.add.noftz.v2.bf16x2, SASS REDG.E.ADD.BF16x4.RN): a row leaves
+// the SM as 2 sectors instead of 4, which is what the backward is bound by.
+template <bool BF16, int LPG, int QPG, class SlotSrc, bool HALF_ACC = false>
 __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(const BwdArgs<SlotSrc> a)
 {
     using X = TapExchange<LPG>;
@@ -110,9 +113,11 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
     // keep the per-lane base as ONE 64-bit register pair: each corner address is then base + u32 offset
     // (IADD3 + IADD3.X) instead of a re-derived IMAD.WIDE chain (5 instructions per address in round 1a)
     asm volatile("" : "+l"(vbase));
-    // grad_value is always fp32: 16 bytes per channel quad; offsets published for `value` scale by 16/kQuadBytes
-    char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * 16u : nullptr;
-    constexpr unsigned kGvShift = BF16 ? 1u : 0u;
+    // grad_value is fp32 unless HALF_ACC: 16 bytes per channel quad; offsets published for `value` scale by 16/kQuadBytes
+    static_assert(!HALF_ACC || BF16, "bf16 accumulation needs bf16 value");
+    constexpr unsigned kGvQuadBytes = HALF_ACC ? 8u : 16u;
+    char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * kGvQuadBytes : nullptr;
+    constexpr unsigned kGvShift = (BF16 && !HALF_ACC) ? 1u : 0u;
     // deterministic mode: 8-byte fixed-point accumulators, same row pitch in elements -> offsets scale by
     // 2 * 16 / kQuadBytes; within a (row, head) the channels are permuted (det_add4): lane j starts at word j
     char *detb = a.det.acc ? reinterpret_cast<char *>(a.det.acc) + (size_t)(m * LPG) * 32u + (size_t)j * 8u : nullptr;
@@ -174,10 +179,10 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                         if (c.z != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.z << (kGvShift + 1))), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
                         if (c.w != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.w << (kGvShift + 1))), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
                     } else if (gvb) {
-                        if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
-                        if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
-                        if (c.z != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.z << kGvShift)), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
-                        if (c.w != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.w << kGvShift)), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                        if (c.x != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.x << kGvShift), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                        if (c.y != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.y << kGvShift), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                        if (c.z != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.z << kGvShift), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                        if (c.w != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.w << kGvShift), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
                     }
                 }
 

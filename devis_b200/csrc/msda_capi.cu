@@ -182,8 +182,11 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
 {
     const OpDims &d = a.d;
     const bool det = (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) && a.grad_value != nullptr;
+    // bf16 grad_value accumulated with packed bf16 reductions: bf16 value, grouped-lane kernels, default mode only
+    const bool half_acc = (flags & DEVIS_MSDA_FLAG_BF16_GRAD_VALUE) && a.grad_value != nullptr;
+    if (half_acc && (dtype != DEVIS_MSDA_BF16 || det || lanes_per_group(dtype, d) == 0)) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const size_t n_value = (size_t)d.outer * d.S * d.M * d.D;
-    float *final_grad_value = a.grad_value;
+    float *final_grad_value = reinterpret_cast<float *>(a.grad_value);
     if (det) {
         if (dtype == DEVIS_MSDA_F64) return DEVIS_MSDA_ERR_UNSUPPORTED;
         const size_t need = det_workspace_bytes(d.outer, d.S, d.M, d.D);
@@ -210,7 +213,7 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
         a.grad_value = nullptr;  // the float reductions are replaced by the fixed-point ones
     }
     if (a.grad_value) {  // the reference's at::zeros_like(value), ms_deform_attn_cuda.cu:121
-        const size_t bytes = (size_t)d.outer * d.S * d.M * d.D * (dtype == DEVIS_MSDA_F64 ? 8 : 4);
+        const size_t bytes = (size_t)d.outer * d.S * d.M * d.D * (dtype == DEVIS_MSDA_F64 ? 8 : half_acc ? 2 : 4);
         if (bytes) {
             const cudaError_t e = cudaMemsetAsync(a.grad_value, 0, bytes, st);
             if (e != cudaSuccess) return cuda_fail(e);
@@ -225,7 +228,7 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
     if (d.outer == 0 || d.Lq == 0) return finalize();
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
     if (lpg) {
-        const LaunchShape s = pick_shape(d.Lq, kShapeBwd, 2, 2, 3);
+        const LaunchShape s = pick_shape(d.Lq, kShapeBwd, half_acc ? 1 : 2, 2, 3);
         smem += exchange_bytes(lpg, s.threads);
         const int qc = s.threads / lpg;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -237,7 +240,10 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
         if (s.qpg == 2) DEVIS_BWD(BF, LPG, 2);      \
         else DEVIS_BWD(BF, LPG, 1);                 \
     } while (0)
-        if (dtype == DEVIS_MSDA_BF16) {
+        if (half_acc) {
+            if (lpg == 8) msda_bwd_kernel<true, 8, 1, SlotSrc, true><<<grid, s.threads, smem, st>>>(a);
+            else msda_bwd_kernel<true, 4, 1, SlotSrc, true><<<grid, s.threads, smem, st>>>(a);
+        } else if (dtype == DEVIS_MSDA_BF16) {
             if (lpg == 8) DEVIS_BWD_Q(true, 8);
             else DEVIS_BWD_Q(true, 4);
         } else {
@@ -376,7 +382,7 @@ int devis_msda_backward(const void *value, const int64_t *spatial_shapes, const 
     BwdArgs<DeviceLevels> a{};
     a.value = value;
     a.grad_out = grad_output;
-    a.grad_value = want_gv ? reinterpret_cast<float *>(grad_value) : nullptr;
+    a.grad_value = want_gv ? grad_value : nullptr;
     a.seg[0] = Segment{sampling_loc, attn_weight, grad_sampling_loc, grad_attn_weight, num_levels, num_point};
     a.n_seg = 1;
     a.n_slots_total = num_levels;
@@ -458,7 +464,7 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     if (rc) return rc;
     a.value = value;
     a.grad_out = grad_output;
-    a.grad_value = want_gv ? reinterpret_cast<float *>(grad_value) : nullptr;
+    a.grad_value = want_gv ? grad_value : nullptr;
     a.seg[0] = Segment{loc_curr, aw_curr, grad_loc_curr, grad_aw_curr, num_levels, n_curr_points};
     a.n_seg = 1;
     a.n_slots_total = num_levels;
@@ -563,9 +569,11 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
     if (rc) return rc;
     if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
+    const bool half_acc = want_gv && (flags & DEVIS_MSDA_FLAG_BF16_GRAD_VALUE);
+    if (half_acc && dtype != DEVIS_MSDA_BF16) return DEVIS_MSDA_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (want_gv) {
-        const size_t bytes = (size_t)num_frames * spatial_size * num_heads * channels * sizeof(float);
+        const size_t bytes = (size_t)num_frames * spatial_size * num_heads * channels * (half_acc ? 2 : sizeof(float));
         if (bytes && !grad_value) return DEVIS_MSDA_ERR_NULL_POINTER;
         if (bytes) {
             const cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, st);
@@ -576,7 +584,7 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
     if (!grad_output || !grad_off_curr || !grad_logit_curr || (a.n_seg > 1 && (!grad_off_temporal || !grad_logit_temporal)))
         return DEVIS_MSDA_ERR_NULL_POINTER;
     a.grad_out = grad_output;
-    a.grad_value = want_gv ? reinterpret_cast<float *>(grad_value) : nullptr;
+    a.grad_value = want_gv ? grad_value : nullptr;
     a.grad_off[0] = reinterpret_cast<float *>(grad_off_curr);
     a.grad_logit[0] = reinterpret_cast<float *>(grad_logit_curr);
     a.grad_off[1] = reinterpret_cast<float *>(grad_off_temporal);
@@ -586,7 +594,8 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
     size_t smem;
     rc = fused_grid(a, 2, grid, threads, smem);
     if (rc) return rc;
-    if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
+    if (half_acc) tmsda_fused_bwd_kernel<true, true><<<grid, threads, smem, st>>>(a);
+    else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
     else tmsda_fused_bwd_kernel<false><<<grid, threads, smem, st>>>(a);
     return check_launch();
 }

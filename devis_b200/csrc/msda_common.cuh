@@ -198,6 +198,23 @@ __device__ __forceinline__ void red_add_f4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// four consecutive bf16 channels as one 8-byte packed reduction (each addend is rounded to bf16, and so is every
+// partial sum at the L2 -- the precision of PyTorch's own bf16 atomicAdd scatter, e.g. grid_sample's backward)
+__device__ __forceinline__ void red_add_bf16x4(void *p, float a, float b, float c, float d)
+{
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1,%2};" ::"l"(p),
+                 "r"(*reinterpret_cast<const unsigned *>(&lo)), "r"(*reinterpret_cast<const unsigned *>(&hi))
+                 : "memory");
+}
+
+template <bool HALF>
+__device__ __forceinline__ void red_add_quad(char *p, float a, float b, float c, float d)
+{
+    if (HALF) red_add_bf16x4(p, a, b, c, d);
+    else red_add_f4(reinterpret_cast<float *>(p), a, b, c, d);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Deterministic grad_value (DEVIS_MSDA_FLAG_DETERMINISTIC).  Floating-point atomics make the
 // reference's grad_value run-to-run different.  Here every contribution

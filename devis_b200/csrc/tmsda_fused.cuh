@@ -36,7 +36,7 @@ struct FusedArgs {
     void *out;
     // backward
     const void *grad_out;
-    float *grad_value;
+    void *grad_value;          // fp32 (bf16 under HALF_ACC)
     float *grad_off[2];
     float *grad_logit[2];
 };
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
     }
 }
 
-template <bool BF16>
+// HALF_ACC: bf16 grad_value with packed bf16 reductions (see msda_bwd_kernel)
+template <bool BF16, bool HALF_ACC = false>
 __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
@@ -162,8 +163,9 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
     const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
     const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
     asm volatile("" : "+l"(vbase));
-    char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * 16u : nullptr;
-    constexpr unsigned kGvShift = BF16 ? 1u : 0u;
+    static_assert(!HALF_ACC || BF16, "bf16 accumulation needs bf16 value");
+    char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * (HALF_ACC ? 8u : 16u) : nullptr;
+    constexpr unsigned kGvShift = (BF16 && !HALF_ACC) ? 1u : 0u;
 
     float rmax, rinv;
     row_softmax_stats(a, row, j, qlive, rmax, rinv);
@@ -210,10 +212,10 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
                 dsum[jj][2] = fmaf(v10.w, gg.w, fmaf(v10.z, gg.z, fmaf(v10.y, gg.y, v10.x * gg.x)));
                 dsum[jj][3] = fmaf(v11.w, gg.w, fmaf(v11.z, gg.z, fmaf(v11.y, gg.y, v11.x * gg.x)));
                 if (gvb) {
-                    if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
-                    if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
-                    if (c.z != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.z << kGvShift)), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
-                    if (c.w != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.w << kGvShift)), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                    if (c.x != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.x << kGvShift), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                    if (c.y != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.y << kGvShift), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                    if (c.z != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.z << kGvShift), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                    if (c.w != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.w << kGvShift), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
                 }
             }
             float A[4];

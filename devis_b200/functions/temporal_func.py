@@ -86,13 +86,15 @@ class TemporalMSDeformAttnFunction(Function):
         t, s, m, d, lq, pc, pt = _dims(value, lc, lt, geometry)
         gout = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
         gout = gout if gout.is_contiguous() else gout.contiguous()
-        acc_dtype = torch.float32 if value.dtype == torch.bfloat16 else value.dtype
         need_gv = ctx.needs_input_grad[0]
+        half_acc = need_gv and MSDA.bf16_accumulate_enabled(value)
+        acc_dtype = torch.float32 if (value.dtype == torch.bfloat16 and not half_acc) else value.dtype
         gv = torch.empty(value.shape, dtype=acc_dtype, device=value.device) if need_gv else None
         glc, gac = torch.empty_like(lc), torch.empty_like(ac)
         glt = torch.empty_like(lt) if has_t else None
         gat = torch.empty_like(at) if has_t else None
-        flags = (_lib.FLAG_DETERMINISTIC if MSDA.deterministic_enabled(value.dtype) else 0) | (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE)
+        flags = (_lib.FLAG_DETERMINISTIC if MSDA.deterministic_enabled(value.dtype) else 0) \
+            | (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE) | (_lib.FLAG_BF16_GRAD_VALUE if half_acc else 0)
         lib = _lib.load()
         code = _DTYPES[value.dtype]
         with torch.cuda.device(value.device):
@@ -168,7 +170,9 @@ class TemporalMSDeformAttnFusedFunction(Function):
         gout = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
         gout = gout if gout.is_contiguous() else gout.contiguous()
         need_gv = ctx.needs_input_grad[0]
-        gv = torch.empty(value.shape, dtype=torch.float32, device=value.device) if need_gv else None
+        half_acc = need_gv and MSDA.bf16_accumulate_enabled(value)
+        gv = torch.empty(value.shape, dtype=value.dtype if half_acc else torch.float32, device=value.device) \
+            if need_gv else None
         goc, glc = torch.empty_like(oc), torch.empty_like(lc)
         got = torch.empty_like(ot) if has_t else None
         glt = torch.empty_like(lt) if has_t else None
@@ -177,7 +181,8 @@ class TemporalMSDeformAttnFusedFunction(Function):
                 _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr, _ptr(ref), _ptr(oc), _ptr(lc),
                 _ptr(ot), _ptr(lt), _ptr(gout), _ptr(gv), _ptr(goc), _ptr(glc), _ptr(got), _ptr(glt), _ptr(query_order),
                 t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0, _DTYPES[value.dtype],
-                0 if need_gv else _lib.FLAG_NO_GRAD_VALUE, torch.cuda.current_stream().cuda_stream))
+                (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE) | (_lib.FLAG_BF16_GRAD_VALUE if half_acc else 0),
+                torch.cuda.current_stream().cuda_stream))
         doc, dlc, dot, dlt = ctx.in_dtypes
         if gv is not None and gv.dtype != value.dtype:
             gv = gv.to(value.dtype)

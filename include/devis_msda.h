@@ -57,6 +57,10 @@ extern "C" {
 /* backward flags */
 #define DEVIS_MSDA_FLAG_DETERMINISTIC 1u   /* bit-reproducible grad_value (no floating-point atomics) */
 #define DEVIS_MSDA_FLAG_NO_GRAD_VALUE 2u   /* skip grad_value (value does not require grad)            */
+#define DEVIS_MSDA_FLAG_BF16_GRAD_VALUE 4u /* DEVIS_MSDA_BF16 only, channels 16 or 32, not with DETERMINISTIC: grad_value is a  */
+                                           /* bf16 tensor like value, accumulated with packed bf16 reductions (every partial  */
+                                           /* sum rounds to bf16, like PyTorch's bf16 atomicAdd scatters); halves the bytes   */
+                                           /* the scatter moves.  Default (flag clear): float grad_value, float accumulation. */
 
 int devis_msda_abi_version(void);
 const char *devis_msda_error_string(int code);
