@@ -46,10 +46,10 @@ class RawClip:
 
     def bwd(self, flags=0):
         c, g = self.c, self.geom
-        ws_ptr, ws_bytes = None, 0
-        if flags & _lib.FLAG_DETERMINISTIC:
-            ws_bytes = int(self.lib.devis_tmsda_backward_workspace_bytes(
-                self.t, self.s, self.m, self.d, g.n_levels, self.lq, self.pc, self.pt, g.t_window, self.code, flags))
+        ws_ptr = None
+        ws_bytes = int(self.lib.devis_tmsda_backward_workspace_bytes(
+            self.t, self.s, self.m, self.d, g.n_levels, self.lq, self.pc, self.pt, g.t_window, self.code, flags))
+        if ws_bytes:
             if self.ws is None or self.ws.numel() < ws_bytes:
                 self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=c["value"].device)
             ws_ptr = self.ws.data_ptr()

@@ -8,6 +8,7 @@
 
 #include "../../include/devis_msda.h"
 #include "msda_bwd.cuh"
+#include "msda_bwd_win.cuh"
 #include "msda_common.cuh"
 #include "msda_fwd.cuh"
 #include "msda_generic.cuh"
@@ -19,7 +20,7 @@ namespace {
 
 std::atomic<uint64_t> g_launches{0};
 thread_local int t_last_cuda_error = 0;
-std::atomic<int> g_tuning[8];
+std::atomic<int> g_tuning[16];
 
 int cuda_fail(cudaError_t e)
 {
@@ -266,6 +267,80 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
     return rc ? rc : finalize();
 }
 
+// ---- windowed whole-clip backward (msda_bwd_win.cuh) -----------------------------------------------------------
+constexpr size_t kWinWorkspaceBytes = 16;   // [u32 unused][u32 bits of max|attn weight|]
+
+size_t window_smem_bytes(int n_slots_total, int budget_rows)
+{
+    return (size_t)n_slots_total * sizeof(int4) + 5 * kMaxLevels * sizeof(int) + 16 +
+           (size_t)(kWinThreads / 32) * (TapExchange<8>::kBytesPerWarp + 64 * sizeof(unsigned)) +
+           (size_t)budget_rows * 32 * sizeof(int);
+}
+
+// The windowed kernel serves the encoder form: one query per pyramid pixel (the caller says so by passing a
+// query_order), D = 32, fp32 / bf16 value with float grad_value, levels stored back to back, every sampled frame's
+// taps a whole number of 8-tap chunks.  EXPERIMENTAL and off by default (tuning key 6 = 2 switches it on): at the DeVIS
+// shape it removes 34 - 41 % of the global reductions but executes 33 % more instructions and keeps the L1 data pipe at
+// 71 %, so it runs in 1.76 ms against 1.43 ms for msda_bwd_kernel (profiles/README.md, round 1h).
+bool window_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, const void *workspace, size_t workspace_bytes)
+{
+    if (g_tuning[6].load() != 2) return false;
+    if (!a.q_perm || !a.grad_value || (flags & (DEVIS_MSDA_FLAG_DETERMINISTIC | DEVIS_MSDA_FLAG_BF16_GRAD_VALUE))) return false;
+    if (!workspace || workspace_bytes < kWinWorkspaceBytes) return false;
+    if (lanes_per_group(dtype, a.d) != 8 || a.d.Lq != a.d.S || a.d.outer == 0) return false;
+    const ClipTable &tb = a.src;
+    int next = 0;
+    for (int l = 0; l < tb.L; ++l) {
+        if (tb.lsi[l] != next) return false;
+        next += tb.H[l] * tb.W[l];
+    }
+    if (next != a.d.S) return false;
+    for (int sg = 0; sg < a.n_seg; ++sg)
+        if ((tb.L * a.seg[sg].P) % 8 != 0 || a.seg[sg].n_slots % tb.L != 0) return false;
+    return true;
+}
+
+int launch_backward_window(const BwdArgs<ClipTable> &a, int dtype, void *workspace, cudaStream_t st)
+{
+    const OpDims &d = a.d;
+    WinArgs w{};
+    w.b = a;
+    int tiles = 0;
+    for (int l = 0; l < a.src.L; ++l) {
+        w.tiles_x[l] = (a.src.W[l] + kWinTile - 1) / kWinTile;
+        w.tile_start[l] = tiles;
+        tiles += w.tiles_x[l] * ((a.src.H[l] + kWinTile - 1) / kWinTile);
+    }
+    w.n_tiles = tiles;
+    w.margin = g_tuning[7].load() > 0 ? g_tuning[7].load() : 6;
+    w.budget_rows = g_tuning[8].load() > 0 ? g_tuning[8].load() : 384;
+    if (w.budget_rows > 1536) w.budget_rows = 1536;
+    unsigned *slots = reinterpret_cast<unsigned *>(workspace);
+    w.aw_max_bits = slots + 1;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, kWinWorkspaceBytes, st);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaMemsetAsync(a.grad_value, 0, (size_t)d.outer * d.S * d.M * d.D * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e);
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const size_t n_aw = (size_t)d.outer * d.Lq * d.M * a.seg[sg].n_slots * a.seg[sg].P;
+        absmax_kernel<false><<<148 * 8, 256, 0, st>>>(a.seg[sg].aw, n_aw, slots + 1);
+        const int rc = check_launch();
+        if (rc) return rc;
+    }
+    const size_t smem = window_smem_bytes(a.n_slots_total, w.budget_rows);
+    const dim3 grid((unsigned)(tiles * d.M), (unsigned)d.outer);
+    if (dtype == DEVIS_MSDA_BF16) {
+        e = cudaFuncSetAttribute(msda_bwdw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        msda_bwdw_kernel<true><<<grid, kWinThreads, smem, st>>>(w);
+    } else {
+        e = cudaFuncSetAttribute(msda_bwdw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        msda_bwdw_kernel<false><<<grid, kWinThreads, smem, st>>>(w);
+    }
+    return check_launch();
+}
+
 int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
 {
     if (dtype != DEVIS_MSDA_F32 && dtype != DEVIS_MSDA_F64 && dtype != DEVIS_MSDA_BF16) return DEVIS_MSDA_ERR_BAD_DTYPE;
@@ -325,7 +400,7 @@ uint64_t devis_msda_launch_count(void) { return g_launches.load(); }
 
 int devis_msda_set_tuning(int key, int value)
 {
-    if (key < 0 || key >= 8) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (key < 0 || key >= 16) return DEVIS_MSDA_ERR_BAD_SHAPE;
     g_tuning[key].store(value);
     return DEVIS_MSDA_OK;
 }
@@ -431,8 +506,9 @@ int devis_tmsda_forward(const void *value, const int64_t *spatial_shapes_host,
 size_t devis_tmsda_backward_workspace_bytes(int num_frames, int spatial_size, int num_heads, int channels, int, int,
                                             int, int, int, int dtype, unsigned flags)
 {
-    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC) || (flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE) || dtype == DEVIS_MSDA_F64)
-        return 0;
+    if ((flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE) || dtype == DEVIS_MSDA_F64) return 0;
+    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC))   // the experimental windowed kernel keeps max|attn weight| there
+        return g_tuning[6].load() == 2 ? kWinWorkspaceBytes : 0;
     return det_workspace_bytes(num_frames, spatial_size, num_heads, channels);
 }
 
@@ -477,6 +553,8 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
     a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
     a.q_perm = query_order;
+    if (window_applicable(a, dtype, flags, workspace, workspace_bytes))
+        return launch_backward_window(a, dtype, workspace, (cudaStream_t)stream);
     return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -97,6 +97,7 @@ __device__ __forceinline__ void build_slots(int4 *s_slot, const ClipTable &tb, c
 struct TapGeom {
     float lh, lw, hh, hw;    // fractional parts and complements (unmasked; the backward needs them)
     int rTL, rTR, rBL, rBR;  // clamped value rows of the 4 corners
+    int y0c, x0c;            // clamped (row, column) of the top-left corner inside its map (window placement)
     unsigned ok;             // bit0 top row, bit1 bottom row, bit2 left column, bit3 right column inside the
                              // map; 0 if the whole tap fails the reference's range test
 };
@@ -119,6 +120,8 @@ __device__ __forceinline__ TapGeom tap_geometry(float x, float y, const int4 slo
                : 0u;
     const int h0c = max(h0, 0), h1c = min(h0 + 1, H - 1), w0c = max(w0, 0), w1c = min(w0 + 1, W - 1);
     const int top = slot.z + h0c * W, bot = slot.z + h1c * W;
+    g.y0c = h0c;
+    g.x0c = w0c;
     g.rTL = top + w0c;
     g.rTR = top + w1c;
     g.rBL = bot + w0c;

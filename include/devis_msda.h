@@ -72,7 +72,10 @@ uint64_t devis_msda_launch_count(void);
  * key 0: forward threads per block, 1: forward queries per lane group,
  * key 2: backward threads per block, 3: backward queries per lane group,
  * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always (A/B testing),
- * key 5: 8-lane forward kernel with 16-byte tap records: 0 = fp32 only (default), 1 = always, 2 = never. */
+ * key 5: 8-lane forward kernel with 16-byte tap records: 0 = fp32 only (default), 1 = always, 2 = never,
+ * key 6: 2 = experimental windowed whole-clip backward (per-block shared-memory pre-aggregation of grad_value in
+ *        32-bit fixed point; encoder form only), anything else = off (default),
+ * key 7: its window margin in pixels (0 = 6), key 8: its shared-memory budget in 128-byte rows (0 = 384). */
 int devis_msda_set_tuning(int key, int value);
 
 /*
