@@ -49,7 +49,13 @@ def main():
     ap.add_argument("--attn", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queries", type=int, default=10)
     ap.add_argument("--out", default="")
+    ap.add_argument("--amp", default="off", choices=["off", "bf16"],
+                    help="bf16: run the step under torch.autocast (Linear layers on the bf16 tensor cores, the attention op "
+                         "on bf16 value; the reference's op rejects bf16, cuda/ms_deform_attn_cuda.cu:64)")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 in the fp32 GEMMs (torch.backends.cuda.matmul.allow_tf32)")
     a = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = bool(a.tf32)
+    torch.backends.cudnn.allow_tf32 = bool(a.tf32)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -81,7 +87,8 @@ def main():
             self.m = model
 
         def forward(self):
-            hs, _, memories, *_ = self.m["trunk"](srcs, masks, pos, self.m["query_embed"].weight)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp == "bf16"):
+                hs, _, memories, *_ = self.m["trunk"](srcs, masks, pos, self.m["query_embed"].weight)
             return hs, memories
 
     net = Step()
@@ -93,7 +100,7 @@ def main():
         def step():
             opt.zero_grad(set_to_none=True)
             hs, memories = net()
-            loss = hs[-1].square().mean() + 1e-3 * sum(m.square().mean() for m in memories)
+            loss = hs[-1].float().square().mean() + 1e-3 * sum(m.float().square().mean() for m in memories)
             loss.backward()
             torch.nn.utils.clip_grad_norm_(net.parameters(), 0.1)
             opt.step()
@@ -105,7 +112,7 @@ def main():
         def eager():
             with torch.no_grad():
                 hs, memories = net()
-            return hs[-1].square().mean()
+            return hs[-1].float().square().mean()
 
         if a.graph:
             side = torch.cuda.Stream()
@@ -146,7 +153,8 @@ def main():
         what = ("training step: fwd+bwd+grad all-reduce+clip+AdamW" if a.mode == "train"
                 else "inference forward (eval, no_grad" + (", one CUDA graph)" if a.graph else ", eager)"))
         res = {"workload": f"DeVIS transformer trunk {what}: 6 enc + 6 dec layers, T=6, S=4820, {a.queries} queries/frame, "
-                           "fp32, synthetic features",
+                           + ("bf16 autocast" if a.amp == "bf16" else "fp32 + TF32 GEMMs" if a.tf32 else "fp32") + ", synthetic features",
+               "amp": a.amp, "tf32": bool(a.tf32),
                "mode": a.mode, "cuda_graph": bool(a.graph), "attention": a.attn, "n_gpus": world, "ms_per_step": ms,
                "clips_per_sec": world / (ms * 1e-3), "frames_per_sec": world * T / (ms * 1e-3), "params": n_params,
                "grad_allreduce_bytes_per_step": n_params * 4 if (world > 1 and a.mode == "train") else 0,

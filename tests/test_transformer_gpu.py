@@ -129,3 +129,45 @@ def test_transformer_forward_replays_as_one_cuda_graph():
         graph.replay()
         hs_e, mem_e = run()
         assert torch.equal(hs_g, hs_e) and torch.equal(mem_g, mem_e), trial
+
+
+def test_temporal_encoder_module_under_bf16_autocast():
+    """torch.autocast(bf16): the Linear layers emit bf16, so the op sees bf16 value and bf16 offsets / logits (the
+    reference's op has no bf16 instantiation, ms_deform_attn_cuda.cu:64).  Output and input gradients must stay within
+    bf16 rounding of the fp32 run, on both the fused-prologue and the unfused path."""
+    from devis_b200 import TemporalMSDeformAttnEncoder, synthetic
+    torch.manual_seed(0)
+    T, shapes_l = 3, ((18, 30), (9, 15))
+    S = sum(h * w for h, w in shapes_l)
+    enc = TemporalMSDeformAttnEncoder(n_frames=T, d_model=256, n_levels=2, t_window=T - 1, n_heads=8, n_curr_points=4,
+                                      n_temporal_points=4).cuda()
+    with torch.no_grad():
+        for lin in (enc.attention_weights, enc.temporal_attention_weights):
+            lin.weight.normal_(0, 0.05)
+    query = torch.randn(T, S, 256, device="cuda")
+    inp = torch.randn(T, S, 256, device="cuda")
+    ref = synthetic.pixel_reference_points(shapes_l, T, "cuda")
+    shapes = torch.tensor(shapes_l, device="cuda")
+    lsi = torch.tensor(synthetic.level_start_index(shapes_l), device="cuda")
+    tshapes = shapes.repeat(T - 1, 1)
+    tlsi = torch.cat([tshapes.new_zeros(1), tshapes.prod(1).cumsum(0)[:-1]])
+    offsets = [torch.tensor([d for d in range(-t, T - t) if d != 0], device="cuda") for t in range(T)]
+    gout = torch.randn(T, S, 256, device="cuda")
+
+    def run(amp, fused):
+        enc.fuse_prologue = fused
+        enc.zero_grad(set_to_none=True)
+        q = query.clone().requires_grad_(True)
+        x = inp.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out, _ = enc(q, ref, x, (shapes, tshapes), (lsi, tlsi), offsets)
+        assert out.dtype == (torch.bfloat16 if amp else torch.float32)
+        out.float().backward(gout)
+        return out.detach().float(), q.grad, x.grad
+
+    want = run(False, True)
+    for fused in (True, False):
+        got = run(True, fused)
+        assert got[1].dtype == torch.float32 and got[2].dtype == torch.float32
+        for g_, w_ in zip(got, want):
+            assert nmax(g_.cpu().numpy(), w_.cpu().numpy()) < 4e-2
