@@ -33,6 +33,9 @@ SIGNATURES = {
     "devis_tmsda_backward": (_i, [_vp] * 15 + [_i] * 10 + [_u, _vp, _sz, _vp]),
     "devis_tmsda_fused_forward": (_i, [_vp] * 11 + [_i] * 10 + [_vp]),
     "devis_tmsda_fused_backward": (_i, [_vp] * 16 + [_i] * 10 + [_u, _vp]),
+    # include/devis_deform_conv.h
+    "devis_dcn_im2col": (_i, [_vp] * 4 + [_i] * 15 + [_vp]),
+    "devis_dcn_col2im": (_i, [_vp] * 7 + [_i] * 15 + [_vp]),
 }
 
 _lib = None

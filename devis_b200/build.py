@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdevis_msda.so")
-SOURCES = [os.path.join(CSRC, "msda_capi.cu")]
+SOURCES = [os.path.join(CSRC, "msda_capi.cu"), os.path.join(CSRC, "deform_conv_capi.cu")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

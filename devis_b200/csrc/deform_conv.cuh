@@ -1,0 +1,246 @@
+// deform_conv.cuh -- modulated deformable convolution (DCNv2) gather / scatter kernels for sm_100a.
+//
+// DeVIS's mask head (src/models/deformable_segmentation.py:244-267, MaskHeadConv :323-380) calls
+// torchvision.ops.deform_conv2d for every 3x3 layer.  torchvision's CUDA op (torchvision/csrc/ops/cuda/
+// deform_conv2d_kernel.cu, a third-party dependency of the reference, pinned at torchvision 0.12 in docs/INSTALL.md)
+// is the 2017 im2col design: NCHW input, one thread per (channel, output pixel) column element, scalar 4-byte gathers
+// whose 4 corners are (H*W) floats apart from the next channel's, scalar atomicAdd scatter in the backward, a
+// 5x5-neighbourhood search per column element for grad_input and a serial loop over channels for grad_offset.
+//
+// Here the same arithmetic (bilinear_interpolate with zero padding, deform_conv2d_kernel.cu `bilinear_interpolate`,
+// `deformable_im2col_kernel`, `deformable_col2im_kernel`, `deformable_col2im_coord_kernel`) is laid out like the
+// attention kernels of this library:
+//   * the input is read CHANNELS-LAST (N, H, W, C): a bilinear corner is one contiguous row of C channels, gathered
+//     with 16-byte loads by a group of G lanes (G = 4..32 by channel count);
+//   * a TAP is one (output pixel, kernel position): the tap's geometry is computed once per lane group, its column
+//     slice (C values) is written contiguously: cols[(pixel * K + k) * C + c] -- the GEMM with the weights stays in
+//     cuBLAS (as torchvision's does, at::addmm), it is not part of this file;
+//   * backward: ONE pass per tap gathers the four corner rows again, forms the four dot products
+//     A_c = sum_ch grad_col[ch] * corner_c[ch] (reduced over the group with shuffles) from which grad_mask and
+//     grad_offset follow in closed form, and scatters grad_input with 16-byte vector reductions
+//     (red.global.add.v4.f32) -- replacing torchvision's three kernels and its scalar atomics;
+//   * grad_offset / grad_mask are written exactly once (no zero fill); only grad_input is zero-filled by the launcher.
+// groups = 1 and offset_groups = 1 (all DeVIS uses); any kernel size, stride, padding, dilation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace devis {
+
+// one 16-byte vector reduction (SASS REDG.E.ADD.F32x4) instead of four scalar atomics
+__device__ __forceinline__ void dcn_red_add_f4(float *p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct DcnDims {
+    int N, H, W, C;       // input, channels-last
+    int Ho, Wo;           // output size
+    int kh, kw, sh, sw, ph, pw, dh, dw;
+};
+
+// geometry of one tap, torchvision's bilinear_interpolate: the sample is void unless -1 < h < H and -1 < w < W; corners
+// outside the map contribute zero.  Rows are clamped in-bounds and their weights zeroed, so loads are unconditional.
+template <typename T>
+struct DcnTap {
+    T w[4];          // bilinear weights of TL, TR, BL, BR with outside corners zeroed
+    T hh, hw, lh, lw;
+    int row[4];      // (y * W + x) of the clamped corners
+    bool ok[4];
+    bool inside;
+};
+
+template <typename T>
+__device__ __forceinline__ DcnTap<T> dcn_tap(T h, T w, int H, int W)
+{
+    DcnTap<T> t;
+    t.inside = h > (T)-1 && w > (T)-1 && h < (T)H && w < (T)W;
+    const T hf = floor(h), wf = floor(w);
+    const int h0 = t.inside ? (int)hf : 0, w0 = t.inside ? (int)wf : 0;
+    t.lh = h - hf;
+    t.lw = w - wf;
+    t.hh = (T)1 - t.lh;
+    t.hw = (T)1 - t.lw;
+    const bool top = t.inside && h0 >= 0, bot = t.inside && h0 + 1 <= H - 1;
+    const bool lef = t.inside && w0 >= 0, rig = t.inside && w0 + 1 <= W - 1;
+    t.ok[0] = top && lef;
+    t.ok[1] = top && rig;
+    t.ok[2] = bot && lef;
+    t.ok[3] = bot && rig;
+    t.w[0] = t.ok[0] ? t.hh * t.hw : (T)0;
+    t.w[1] = t.ok[1] ? t.hh * t.lw : (T)0;
+    t.w[2] = t.ok[2] ? t.lh * t.hw : (T)0;
+    t.w[3] = t.ok[3] ? t.lh * t.lw : (T)0;
+    const int h0c = max(h0, 0), h1c = min(h0 + 1, H - 1), w0c = max(w0, 0), w1c = min(w0 + 1, W - 1);
+    t.row[0] = h0c * W + w0c;
+    t.row[1] = h0c * W + w1c;
+    t.row[2] = h1c * W + w0c;
+    t.row[3] = h1c * W + w1c;
+    return t;
+}
+
+// tap index -> (n, k, ho, wo) with wo fastest: the groups of a warp work on neighbouring output pixels for the same
+// kernel position, so their offset / mask reads are coalesced and their gathers share a neighbourhood of the input
+struct DcnTapId {
+    int n, k, ho, wo;
+    long long pixel;   // (n * Ho + ho) * Wo + wo
+};
+
+__device__ __forceinline__ DcnTapId dcn_tap_id(long long tap, const DcnDims &d)
+{
+    DcnTapId id;
+    const int K = d.kh * d.kw;
+    id.wo = (int)(tap % d.Wo);
+    long long r = tap / d.Wo;
+    id.ho = (int)(r % d.Ho);
+    r /= d.Ho;
+    id.k = (int)(r % K);
+    id.n = (int)(r / K);
+    id.pixel = ((long long)id.n * d.Ho + id.ho) * d.Wo + id.wo;
+    return id;
+}
+
+template <typename T>
+__device__ __forceinline__ void dcn_sample_point(const T *offset, const T *mask, const DcnTapId &id, const DcnDims &d,
+                                                 T &h, T &w, T &m)
+{
+    const int K = d.kh * d.kw;
+    const long long plane = (long long)d.Ho * d.Wo;
+    const long long at = (long long)id.ho * d.Wo + id.wo;
+    const T off_h = offset[((long long)id.n * 2 * K + 2 * id.k) * plane + at];
+    const T off_w = offset[((long long)id.n * 2 * K + 2 * id.k + 1) * plane + at];
+    m = mask ? mask[((long long)id.n * K + id.k) * plane + at] : (T)1;
+    const int ky = id.k / d.kw, kx = id.k - ky * d.kw;
+    h = (T)(id.ho * d.sh - d.ph + ky * d.dh) + off_h;
+    w = (T)(id.wo * d.sw - d.pw + kx * d.dw) + off_w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward gather: cols[(pixel * K + k) * C + c] = mask * bilinear(input[n, :, :, c], h, w)
+// V = channels per lane and load (4: float4, C % 4 == 0; 1: any C / double)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int V, int G>
+__global__ void __launch_bounds__(256) dcn_im2col_kernel(const T *__restrict__ input, const T *__restrict__ offset,
+                                                         const T *__restrict__ mask, T *__restrict__ cols, DcnDims d,
+                                                         long long n_taps)
+{
+    const int j = threadIdx.x % G;
+    const long long tap = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (tap >= n_taps) return;
+    const DcnTapId id = dcn_tap_id(tap, d);
+    T h, w, m;
+    dcn_sample_point(offset, mask, id, d, h, w, m);
+    const DcnTap<T> t = dcn_tap(h, w, d.H, d.W);
+    const T *img = input + (long long)id.n * d.H * d.W * d.C;
+    T *out = cols + (id.pixel * (d.kh * d.kw) + id.k) * (long long)d.C;
+    const T f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
+    if (V == 4) {
+        const float4 *r0 = reinterpret_cast<const float4 *>(img + (long long)t.row[0] * d.C);
+        const float4 *r1 = reinterpret_cast<const float4 *>(img + (long long)t.row[1] * d.C);
+        const float4 *r2 = reinterpret_cast<const float4 *>(img + (long long)t.row[2] * d.C);
+        const float4 *r3 = reinterpret_cast<const float4 *>(img + (long long)t.row[3] * d.C);
+        float4 *o = reinterpret_cast<float4 *>(out);
+        for (int c = j; c < d.C / 4; c += G) {
+            const float4 a = __ldg(r0 + c), b = __ldg(r1 + c), e = __ldg(r2 + c), f = __ldg(r3 + c);
+            float4 v;
+            v.x = f0 * a.x + f1 * b.x + f2 * e.x + f3 * f.x;
+            v.y = f0 * a.y + f1 * b.y + f2 * e.y + f3 * f.y;
+            v.z = f0 * a.z + f1 * b.z + f2 * e.z + f3 * f.z;
+            v.w = f0 * a.w + f1 * b.w + f2 * e.w + f3 * f.w;
+            o[c] = v;
+        }
+    } else {
+        const T *r0 = img + (long long)t.row[0] * d.C, *r1 = img + (long long)t.row[1] * d.C;
+        const T *r2 = img + (long long)t.row[2] * d.C, *r3 = img + (long long)t.row[3] * d.C;
+        for (int c = j; c < d.C; c += G) out[c] = f0 * r0[c] + f1 * r1[c] + f2 * r2[c] + f3 * r3[c];
+    }
+}
+
+__device__ __forceinline__ void dcn_red_add(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void dcn_red_add(double *p, double v) { atomicAdd(p, v); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward: grad_input (scatter), grad_offset, grad_mask from grad_cols, one pass per tap
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int V, int G>
+__global__ void __launch_bounds__(256) dcn_col2im_kernel(const T *__restrict__ input, const T *__restrict__ offset,
+                                                         const T *__restrict__ mask, const T *__restrict__ grad_cols,
+                                                         T *__restrict__ grad_input, T *__restrict__ grad_offset,
+                                                         T *__restrict__ grad_mask, DcnDims d, long long n_taps)
+{
+    const int j = threadIdx.x % G;
+    long long tap = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool live = tap < n_taps;
+    if (!live) tap = n_taps - 1;   // keep the whole warp in the shuffles below; results of dead groups are dropped
+    const DcnTapId id = dcn_tap_id(tap, d);
+    T h, w, m;
+    dcn_sample_point(offset, mask, id, d, h, w, m);
+    const DcnTap<T> t = dcn_tap(h, w, d.H, d.W);
+    const T *img = input + (long long)id.n * d.H * d.W * d.C;
+    T *gimg = grad_input ? grad_input + (long long)id.n * d.H * d.W * d.C : nullptr;
+    const T *gc = grad_cols + (id.pixel * (d.kh * d.kw) + id.k) * (long long)d.C;
+    const T f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
+    T A0 = 0, A1 = 0, A2 = 0, A3 = 0;
+    if (V == 4) {
+        const float4 *r0 = reinterpret_cast<const float4 *>(img + (long long)t.row[0] * d.C);
+        const float4 *r1 = reinterpret_cast<const float4 *>(img + (long long)t.row[1] * d.C);
+        const float4 *r2 = reinterpret_cast<const float4 *>(img + (long long)t.row[2] * d.C);
+        const float4 *r3 = reinterpret_cast<const float4 *>(img + (long long)t.row[3] * d.C);
+        const float4 *g4 = reinterpret_cast<const float4 *>(gc);
+        for (int c = j; c < d.C / 4; c += G) {
+            const float4 g = __ldg(g4 + c);
+            const float4 a = __ldg(r0 + c), b = __ldg(r1 + c), e = __ldg(r2 + c), f = __ldg(r3 + c);
+            A0 += g.x * a.x + g.y * a.y + g.z * a.z + g.w * a.w;
+            A1 += g.x * b.x + g.y * b.y + g.z * b.z + g.w * b.w;
+            A2 += g.x * e.x + g.y * e.y + g.z * e.z + g.w * e.w;
+            A3 += g.x * f.x + g.y * f.y + g.z * f.z + g.w * f.w;
+            if (live && gimg) {
+                float *q = reinterpret_cast<float *>(gimg);
+                if (f0 != 0.f) dcn_red_add_f4(q + (long long)t.row[0] * d.C + 4 * c, f0 * g.x, f0 * g.y, f0 * g.z, f0 * g.w);
+                if (f1 != 0.f) dcn_red_add_f4(q + (long long)t.row[1] * d.C + 4 * c, f1 * g.x, f1 * g.y, f1 * g.z, f1 * g.w);
+                if (f2 != 0.f) dcn_red_add_f4(q + (long long)t.row[2] * d.C + 4 * c, f2 * g.x, f2 * g.y, f2 * g.z, f2 * g.w);
+                if (f3 != 0.f) dcn_red_add_f4(q + (long long)t.row[3] * d.C + 4 * c, f3 * g.x, f3 * g.y, f3 * g.z, f3 * g.w);
+            }
+        }
+    } else {
+        const T *r0 = img + (long long)t.row[0] * d.C, *r1 = img + (long long)t.row[1] * d.C;
+        const T *r2 = img + (long long)t.row[2] * d.C, *r3 = img + (long long)t.row[3] * d.C;
+        for (int c = j; c < d.C; c += G) {
+            const T g = gc[c];
+            A0 += g * r0[c];
+            A1 += g * r1[c];
+            A2 += g * r2[c];
+            A3 += g * r3[c];
+            if (live && gimg) {
+                if (f0 != (T)0) dcn_red_add(gimg + (long long)t.row[0] * d.C + c, f0 * g);
+                if (f1 != (T)0) dcn_red_add(gimg + (long long)t.row[1] * d.C + c, f1 * g);
+                if (f2 != (T)0) dcn_red_add(gimg + (long long)t.row[2] * d.C + c, f2 * g);
+                if (f3 != (T)0) dcn_red_add(gimg + (long long)t.row[3] * d.C + c, f3 * g);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) {
+        A0 += __shfl_xor_sync(0xffffffffu, A0, o, G);
+        A1 += __shfl_xor_sync(0xffffffffu, A1, o, G);
+        A2 += __shfl_xor_sync(0xffffffffu, A2, o, G);
+        A3 += __shfl_xor_sync(0xffffffffu, A3, o, G);
+    }
+    if (live && j == 0) {
+        // outside corners carry garbage from their clamped rows: zero them like the zero padding does
+        A0 = t.ok[0] ? A0 : (T)0;
+        A1 = t.ok[1] ? A1 : (T)0;
+        A2 = t.ok[2] ? A2 : (T)0;
+        A3 = t.ok[3] ? A3 : (T)0;
+        const int K = d.kh * d.kw;
+        const long long plane = (long long)d.Ho * d.Wo, at = (long long)id.ho * d.Wo + id.wo;
+        const T val = t.hh * (t.hw * A0 + t.lw * A1) + t.lh * (t.hw * A2 + t.lw * A3);
+        const T gh = t.hw * (A2 - A0) + t.lw * (A3 - A1);      // d/dh of the interpolated value
+        const T gw = t.hh * (A1 - A0) + t.lh * (A3 - A2);      // d/dw
+        grad_offset[((long long)id.n * 2 * K + 2 * id.k) * plane + at] = t.inside ? m * gh : (T)0;
+        grad_offset[((long long)id.n * 2 * K + 2 * id.k + 1) * plane + at] = t.inside ? m * gw : (T)0;
+        if (grad_mask) grad_mask[((long long)id.n * K + id.k) * plane + at] = t.inside ? val : (T)0;
+    }
+}
+
+}  // namespace devis

@@ -1,0 +1,110 @@
+// deform_conv_capi.cu -- C ABI (include/devis_deform_conv.h) of the modulated deformable convolution kernels.
+#include "../../include/devis_deform_conv.h"
+#include "capi_common.h"
+#include "deform_conv.cuh"
+
+using namespace devis;
+
+namespace {
+
+int check_dims(const DcnDims &d, int dtype)
+{
+    if (dtype != DEVIS_MSDA_F32 && dtype != DEVIS_MSDA_F64) return DEVIS_MSDA_ERR_BAD_DTYPE;
+    if (d.N < 0 || d.H <= 0 || d.W <= 0 || d.C <= 0 || d.Ho < 0 || d.Wo < 0 || d.kh <= 0 || d.kw <= 0 || d.sh <= 0 ||
+        d.sw <= 0 || d.ph < 0 || d.pw < 0 || d.dh <= 0 || d.dw <= 0)
+        return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if ((long long)d.H * d.W >= (1LL << 31)) return DEVIS_MSDA_ERR_TOO_LARGE;
+    return DEVIS_MSDA_OK;
+}
+
+// lanes per tap: a group covers its channels in 16-byte pieces; 8 lanes = one 128-byte line per corner row
+template <class F4, class F8, class S8, class S32>
+int dispatch(const DcnDims &d, int dtype, long long n_taps, F4 f4, F8 f8, S8 s8, S32 s32)
+{
+    if (n_taps == 0) return DEVIS_MSDA_OK;
+    int G;
+    const bool vec = dtype == DEVIS_MSDA_F32 && d.C % 4 == 0;
+    if (vec) G = d.C / 4 >= 8 ? 8 : 4;
+    else G = d.C >= 32 ? 32 : 8;
+    const long long blocks = (n_taps * G + 255) / 256;
+    if (blocks > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    if (vec) {
+        if (G == 8) f8((unsigned)blocks);
+        else f4((unsigned)blocks);
+    } else {
+        if (G == 32) s32((unsigned)blocks);
+        else s8((unsigned)blocks);
+    }
+    return devis_capi_check_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+int devis_dcn_im2col(const void *input, const void *offset, const void *mask, void *cols, int batch, int height,
+                     int width, int channels, int out_h, int out_w, int kernel_h, int kernel_w, int stride_h,
+                     int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int dtype, void *stream)
+{
+    const DcnDims d{batch, height, width, channels, out_h, out_w, kernel_h, kernel_w,
+                    stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
+    const int rc = check_dims(d, dtype);
+    if (rc) return rc;
+    const long long n_taps = (long long)batch * out_h * out_w * kernel_h * kernel_w;
+    if (n_taps > 0 && (!input || !offset || !cols)) return DEVIS_MSDA_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DEVIS_MSDA_F32) {
+        const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
+        float *co = (float *)cols;
+        return dispatch(d, dtype, n_taps,
+                        [&](unsigned b) { dcn_im2col_kernel<float, 4, 4><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
+                        [&](unsigned b) { dcn_im2col_kernel<float, 4, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
+                        [&](unsigned b) { dcn_im2col_kernel<float, 1, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
+                        [&](unsigned b) { dcn_im2col_kernel<float, 1, 32><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); });
+    }
+    const double *in = (const double *)input, *of = (const double *)offset, *mk = (const double *)mask;
+    double *co = (double *)cols;
+    return dispatch(d, dtype, n_taps, [&](unsigned) {}, [&](unsigned) {},
+                    [&](unsigned b) { dcn_im2col_kernel<double, 1, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
+                    [&](unsigned b) { dcn_im2col_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); });
+}
+
+int devis_dcn_col2im(const void *input, const void *offset, const void *mask, const void *grad_cols, void *grad_input,
+                     void *grad_offset, void *grad_mask, int batch, int height, int width, int channels, int out_h,
+                     int out_w, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
+                     int dil_w, int dtype, void *stream)
+{
+    const DcnDims d{batch, height, width, channels, out_h, out_w, kernel_h, kernel_w,
+                    stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
+    const int rc = check_dims(d, dtype);
+    if (rc) return rc;
+    const long long n_taps = (long long)batch * out_h * out_w * kernel_h * kernel_w;
+    if (n_taps > 0 && (!input || !offset || !grad_cols || !grad_offset || (mask && !grad_mask)))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_input) {   // torchvision: at::zeros_like(input)
+        const size_t bytes = (size_t)batch * height * width * channels * (dtype == DEVIS_MSDA_F64 ? 8 : 4);
+        if (bytes) {
+            const cudaError_t e = cudaMemsetAsync(grad_input, 0, bytes, st);
+            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+        }
+    }
+    if (dtype == DEVIS_MSDA_F32) {
+        const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
+        const float *gc = (const float *)grad_cols;
+        float *gi = (float *)grad_input, *go = (float *)grad_offset, *gm = (float *)grad_mask;
+        return dispatch(d, dtype, n_taps,
+                        [&](unsigned b) { dcn_col2im_kernel<float, 4, 4><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
+                        [&](unsigned b) { dcn_col2im_kernel<float, 4, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
+                        [&](unsigned b) { dcn_col2im_kernel<float, 1, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
+                        [&](unsigned b) { dcn_col2im_kernel<float, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); });
+    }
+    const double *in = (const double *)input, *of = (const double *)offset, *mk = (const double *)mask;
+    const double *gc = (const double *)grad_cols;
+    double *gi = (double *)grad_input, *go = (double *)grad_offset, *gm = (double *)grad_mask;
+    return dispatch(d, dtype, n_taps, [&](unsigned) {}, [&](unsigned) {},
+                    [&](unsigned b) { dcn_col2im_kernel<double, 1, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
+                    [&](unsigned b) { dcn_col2im_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); });
+}
+
+}  // extern "C"

@@ -14,6 +14,8 @@
 #include "msda_generic.cuh"
 #include "tmsda_fused.cuh"
 
+#include "capi_common.h"
+
 using namespace devis;
 
 namespace {
@@ -22,18 +24,26 @@ std::atomic<uint64_t> g_launches{0};
 thread_local int t_last_cuda_error = 0;
 std::atomic<int> g_tuning[16];
 
-int cuda_fail(cudaError_t e)
+}  // namespace
+
+// shared with the other translation units of the library (capi_common.h)
+int devis_capi_cuda_fail(cudaError_t e)
 {
     t_last_cuda_error = (int)e;
     return DEVIS_MSDA_ERR_CUDA;
 }
 
-int check_launch()
+int devis_capi_check_launch()
 {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? DEVIS_MSDA_OK : cuda_fail(e);
+    return e == cudaSuccess ? DEVIS_MSDA_OK : devis_capi_cuda_fail(e);
 }
+
+namespace {
+
+int cuda_fail(cudaError_t e) { return devis_capi_cuda_fail(e); }
+int check_launch() { return devis_capi_check_launch(); }
 
 size_t elem_size(int dtype) { return dtype == DEVIS_MSDA_F64 ? 8 : dtype == DEVIS_MSDA_BF16 ? 2 : 4; }
 

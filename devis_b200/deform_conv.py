@@ -1,0 +1,123 @@
+"""Modulated deformable convolution for DeVIS's mask head: ``deform_conv2d`` with torchvision's signature.
+
+The reference calls ``torchvision.ops.deform_conv2d(input, offset, weight, bias, padding=..., mask=...)`` in
+ModulatedDeformableConv2d.forward (src/models/deformable_segmentation.py:262-267).  torchvision's operator
+(torchvision/ops/deform_conv.py:14-99, C++ vision::ops::deform_conv2d) computes
+
+    out[n, co, y, x] = bias[co] + sum_{ci, k} weight[co, ci, k] * mask[n, k, y, x] *
+                       bilinear(input[n, ci], y*stride - pad + ky*dil + offset[n, 2k, y, x],
+                                               x*stride - pad + kx*dil + offset[n, 2k+1, y, x])
+
+with zero padding.  Here the gather (and, backward, the scatter plus the offset / mask gradients) are the hand-written
+sm_100a kernels behind ``devis_dcn_im2col`` / ``devis_dcn_col2im`` (include/devis_deform_conv.h,
+devis_b200/csrc/deform_conv.cuh); the contractions with ``weight`` are cuBLAS GEMMs, as in torchvision (at::addmm).
+The input is read channels-last: pass a ``torch.channels_last`` tensor to avoid the layout copy; the result is returned
+as an NCHW view of a channels-last buffer.
+
+Supported: groups == 1 and offset_groups == 1 (everything DeVIS uses), float32 / float64 (half and bfloat16 are
+computed in float32 like torchvision's autocast wrapper does), CUDA only -- there is no CPU fallback.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() else None
+
+
+def _out_size(size, k, stride, pad, dil):
+    return (size + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+class DeformConv2dFunction(Function):
+    """apply(input, offset, weight, bias, mask, stride, padding, dilation) -> (N, Cout, Ho, Wo)"""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, bias, mask, stride, padding, dilation):
+        n, c, h, w = input.shape
+        cout, _, kh, kw = weight.shape
+        (sh, sw), (ph, pw), (dh, dw) = stride, padding, dilation
+        ho, wo = _out_size(h, kh, sh, ph, dh), _out_size(w, kw, sw, pw, dw)
+        x = input.permute(0, 2, 3, 1)
+        x = x if x.is_contiguous() else x.contiguous()                    # (N, H, W, C)
+        offset = offset if offset.is_contiguous() else offset.contiguous()
+        if mask is not None:
+            mask = mask if mask.is_contiguous() else mask.contiguous()
+        k = kh * kw
+        cols = torch.empty((n * ho * wo, k * c), dtype=input.dtype, device=input.device)
+        dims = (n, h, w, c, ho, wo, kh, kw, sh, sw, ph, pw, dh, dw)
+        with torch.cuda.device(input.device):
+            _lib.check(_lib.load().devis_dcn_im2col(_ptr(x), _ptr(offset), _ptr(mask), _ptr(cols), *dims,
+                                                    _DTYPES[input.dtype], torch.cuda.current_stream().cuda_stream))
+        w2 = weight.permute(0, 2, 3, 1).reshape(cout, k * c)              # columns are [k][ci]
+        out = torch.addmm(bias, cols, w2.t()) if bias is not None else cols @ w2.t()
+        ctx.dims = dims
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, offset, mask, cols, w2)
+        return out.view(n, ho, wo, cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, offset, mask, cols, w2 = ctx.saved_tensors
+        n, h, w, c, ho, wo, kh, kw = ctx.dims[:8]
+        cout = w2.shape[0]
+        g2 = grad_out.permute(0, 2, 3, 1).reshape(n * ho * wo, cout)
+        need_in, need_off, need_w, need_b, need_m = ctx.needs_input_grad[:5]
+        grad_w = grad_b = grad_in = grad_off = grad_m = None
+        if need_w:
+            grad_w = (g2.t() @ cols).view(cout, kh, kw, c).permute(0, 3, 1, 2)
+        if need_b and ctx.has_bias:
+            grad_b = g2.sum(0)
+        if need_in or need_off or (need_m and mask is not None):
+            grad_cols = g2 @ w2
+            gx = torch.empty_like(x) if need_in else None
+            grad_off = torch.empty_like(offset)
+            grad_m = torch.empty_like(mask) if mask is not None else None
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().devis_dcn_col2im(_ptr(x), _ptr(offset), _ptr(mask), _ptr(grad_cols), _ptr(gx),
+                                                        _ptr(grad_off), _ptr(grad_m), *ctx.dims, _DTYPES[x.dtype],
+                                                        torch.cuda.current_stream().cuda_stream))
+            grad_in = gx.permute(0, 3, 1, 2) if need_in else None
+        return grad_in, grad_off, grad_w, grad_b, grad_m, None, None, None
+
+
+def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None):
+    """torchvision.ops.deform_conv2d (torchvision/ops/deform_conv.py:14), same arguments and result."""
+    stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
+    if input.dim() != 4 or weight.dim() != 4 or offset.dim() != 4:
+        raise RuntimeError("deform_conv2d: input, offset and weight must be 4-dimensional")
+    if not input.is_cuda:
+        raise RuntimeError("deform_conv2d: not implemented on the CPU (no fallback in this library)")
+    n, c, h, w = input.shape
+    cout, cin_g, kh, kw = weight.shape
+    if cin_g != c:
+        raise RuntimeError(f"deform_conv2d: groups = {c // max(cin_g, 1)} is not supported by this build (groups = 1 only)")
+    if offset.shape[1] != 2 * kh * kw:
+        if offset.shape[1] % (2 * kh * kw) == 0 and offset.shape[1] > 0:
+            raise RuntimeError("deform_conv2d: offset_groups > 1 is not supported by this build")
+        raise RuntimeError(f"deform_conv2d: offset.shape[1] must be 2 * kernel_h * kernel_w = {2 * kh * kw}, got {offset.shape[1]}")
+    ho, wo = _out_size(h, kh, stride[0], padding[0], dilation[0]), _out_size(w, kw, stride[1], padding[1], dilation[1])
+    if ho <= 0 or wo <= 0:
+        raise RuntimeError(f"deform_conv2d: calculated output size too small ({ho} x {wo})")
+    if tuple(offset.shape) != (n, 2 * kh * kw, ho, wo):
+        raise RuntimeError(f"deform_conv2d: offset must be {(n, 2 * kh * kw, ho, wo)}, got {tuple(offset.shape)}")
+    if mask is not None and tuple(mask.shape) != (n, kh * kw, ho, wo):
+        raise RuntimeError(f"deform_conv2d: mask must be {(n, kh * kw, ho, wo)}, got {tuple(mask.shape)}")
+    if bias is not None and tuple(bias.shape) != (cout,):
+        raise RuntimeError("deform_conv2d: bias must have out_channels elements")
+    out_dtype = input.dtype
+    if out_dtype in (torch.float16, torch.bfloat16):          # torchvision's autocast wrapper computes in float32 too
+        cast = lambda t: None if t is None else t.float()
+        input, offset, weight, bias, mask = cast(input), cast(offset), cast(weight), cast(bias), cast(mask)
+    elif out_dtype not in _DTYPES:
+        raise RuntimeError(f'"deform_conv2d" not implemented for \'{out_dtype}\'')
+    same = lambda t: None if t is None else (t if t.dtype == input.dtype else t.to(input.dtype))
+    out = DeformConv2dFunction.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
+    return out if out.dtype == out_dtype else out.to(out_dtype)

@@ -17,6 +17,11 @@ reference's own Python code executed here:
               layers, 2 temporal decoder layers with iterative box refinement) on a small padded clip:
               every output of its forward, input gradients and all parameter gradients, float64
 
+  dcn_*.npz   torchvision.ops.deform_conv2d (the operator the reference's mask head calls,
+              deformable_segmentation.py:265) on CPU, forward and autograd backward, float64; and the
+              reference's own ModulatedDeformableConv2d / MaskHeadConv modules (deformable_segmentation.py:244-380)
+              with their state_dict  [--only-dcn regenerates just these]
+
 Usage:  python tests/golden/make_golden.py
 """
 import importlib
@@ -369,11 +374,88 @@ def make_trunk_fixtures(devis_tr):
     torch.set_default_dtype(torch.float32)
 
 
+def import_reference_mask_head():
+    """refsrc.models.deformable_segmentation with permissive stubs for the packages this image lacks
+    (pycocotools, yacs, matplotlib, ... -- none of them is touched by the two classes used here)."""
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return type(k, (), {})
+    for _ in range(40):
+        try:
+            return importlib.import_module("refsrc.models.deformable_segmentation")
+        except ModuleNotFoundError as exc:
+            sys.modules[exc.name] = _Any(exc.name)
+    raise RuntimeError("could not import the reference mask head")
+
+
+def make_dcn_fixtures(seg):
+    from torchvision.ops import deform_conv2d
+    gen = torch.Generator().manual_seed(11)
+    rn = lambda *s: torch.randn(*s, generator=gen, dtype=torch.float64)
+    # name: (N, Cin, Cout, H, W, k, stride, pad, dil, mask, offset scale)
+    cases = {
+        "dcn_k3_mask": (2, 8, 5, 7, 9, 3, 1, 1, 1, True, 1.5),          # the DeVIS configuration (3x3, pad 1, modulated)
+        "dcn_k3_c24": (1, 24, 6, 6, 8, 3, 1, 1, 1, True, 3.0),          # 4-lane vector path, taps leaving the map
+        "dcn_k3_c40": (1, 40, 7, 5, 6, 3, 1, 1, 1, True, 1.0),          # 8-lane vector path, ragged last piece
+        "dcn_stride2_dil2_nomask": (2, 6, 4, 9, 8, 3, 2, 2, 2, False, 1.0),
+        "dcn_k1": (1, 3, 2, 5, 5, 1, 1, 0, 1, True, 0.7),
+        "dcn_c33": (1, 33, 3, 4, 5, 3, 1, 1, 1, True, 1.0),             # scalar path, 32 lanes
+    }
+    for name, (n, cin, cout, h, w, k, st, pd, dl, use_mask, osc) in cases.items():
+        ho = (h + 2 * pd - (dl * (k - 1) + 1)) // st + 1
+        wo = (w + 2 * pd - (dl * (k - 1) + 1)) // st + 1
+        x, wt, b = rn(n, cin, h, w), rn(cout, cin, k, k), rn(cout)
+        off = osc * rn(n, 2 * k * k, ho, wo)
+        m = torch.rand(n, k * k, ho, wo, generator=gen, dtype=torch.float64) * 2 if use_mask else None
+        leaves = [t.clone().requires_grad_(True) for t in (x, off, wt, b)] + ([m.clone().requires_grad_(True)] if use_mask else [])
+        out = deform_conv2d(leaves[0], leaves[1], leaves[2], leaves[3], stride=st, padding=pd, dilation=dl,
+                            mask=leaves[4] if use_mask else None)
+        gout = rn(*out.shape)
+        out.backward(gout)
+        arrays = dict(x=x, offset=off, weight=wt, bias=b, gout=gout, out=out, gx=leaves[0].grad, goffset=leaves[1].grad,
+                      gweight=leaves[2].grad, gbias=leaves[3].grad, cfg=np.array([st, pd, dl, int(use_mask)]))
+        if use_mask:
+            arrays.update(mask=m, gmask=leaves[4].grad)
+        save(name, **arrays)
+
+    # the reference's modules (float64): one modulated layer, and the whole FPN-style head with deformable layers
+    torch.set_default_dtype(torch.float64)
+    layer = seg.ModulatedDeformableConv2d(12, 8, 3, padding=1, bias=True)
+    randomize(layer, gen)
+    x = rn(2, 12, 7, 6).requires_grad_(True)
+    y = layer(x)
+    gout = rn(*y.shape)
+    y.backward(gout)
+    save("dcn_mod_layer", x=x, out=y, gout=gout, gx=x.grad, **sd_arrays(layer),
+         **{"pg." + k: p.grad for k, p in layer.named_parameters()})
+
+    dim, nheads, fpn_dims, n_inst = 64, 8, [24, 16], 2
+    head = seg.MaskHeadConv(dim, fpn_dims, nheads, True, ["/32", "/16"], 2)
+    randomize(head, gen)
+    sizes = [(3, 4), (6, 8), (12, 16)]
+    feats = [rn(1, ch, *sz).requires_grad_(True) for ch, sz in zip([dim] + fpn_dims, sizes)]
+    att = [rn(n_inst, nheads, *sz) for sz in sizes[:2]]
+    expand = lambda t, n: t.unsqueeze(1).repeat(1, int(n), 1, 1, 1).flatten(0, 1)
+    y = head(feats, att, n_inst, expand)
+    gout = rn(*y.shape)
+    y.backward(gout)
+    save("dcn_mask_head", out=y, gout=gout, cfg=np.array([dim, nheads, n_inst] + fpn_dims),
+         **{f"feat{i}": f for i, f in enumerate(feats)}, **{f"gfeat{i}": f.grad for i, f in enumerate(feats)},
+         **{f"att{i}": a for i, a in enumerate(att)}, **sd_arrays(head))
+    torch.set_default_dtype(torch.float32)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("the reference is not mounted; fixtures can only be regenerated in the build container")
     func_mod, mods_mod, devis_tr_mod, def_tr_mod = import_reference()
+    if "--only-dcn" in sys.argv:
+        make_dcn_fixtures(import_reference_mask_head())
+        sys.exit(0)
     if "--only-trunk" not in sys.argv:
         make_op_fixtures(func_mod)
         make_module_fixtures(mods_mod, devis_tr_mod, def_tr_mod)
     make_trunk_fixtures(devis_tr_mod)
+    make_dcn_fixtures(import_reference_mask_head())

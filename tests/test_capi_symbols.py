@@ -7,12 +7,14 @@ import re
 from conftest import ROOT
 
 HEADER = os.path.join(ROOT, "include", "devis_msda.h")
+HEADERS = [HEADER, os.path.join(ROOT, "include", "devis_deform_conv.h")]
 
 
 def _declared_functions():
-    text = open(HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"\b(devis_t?msda_\w+)\s*\(", text)
+    names = []
+    for path in HEADERS:
+        text = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        names += re.findall(r"\b(devis_(?:t?msda|dcn)_\w+)\s*\(", text)
     return sorted(set(names))
 
 
@@ -21,9 +23,9 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     build.build()
     lib = ctypes.CDLL(_lib.LIB_PATH)
     declared = _declared_functions()
-    assert len(declared) >= 11
+    assert len(declared) >= 13 and "devis_dcn_im2col" in declared
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in devis_msda.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "python binding and header disagree on the function list"
 
 
@@ -54,6 +56,13 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.devis_msda_forward(null, null, null, null, null, null, 1, 4, 2, 32, 1, 1, 1, 64, 0, null) == -1
     assert lib.devis_msda_backward(null, null, null, null, null, null, null, null, null, 1, 4, 2, 32, 1, 1, 1, 64, 0,
                                    0, null, 0, null) == -1
+    # deformable-convolution entry points: dtype (bf16 is not served), shape, null pointers
+    dims = (1, 4, 4, 8, 4, 4, 3, 3, 1, 1, 1, 1, 1, 1)
+    assert lib.devis_dcn_im2col(null, null, null, null, *dims, 2, null) == -3
+    assert lib.devis_dcn_im2col(null, null, null, null, *((1, 0) + dims[2:]), 0, null) == -2
+    assert lib.devis_dcn_im2col(null, null, null, null, *dims, 0, null) == -1
+    assert lib.devis_dcn_col2im(null, null, null, null, null, null, null, *dims, 0, null) == -1
+    assert lib.devis_dcn_im2col(null, null, null, null, *((0,) + dims[1:]), 0, null) == 0
     # empty problems are fine with null pointers and launch nothing
     before = lib.devis_msda_launch_count()
     assert lib.devis_msda_forward(null, null, null, null, null, null, 0, 4, 2, 32, 1, 0, 1, 64, 0, null) == 0

@@ -1,0 +1,160 @@
+"""GPU parity of the modulated deformable convolution (devis_b200.deform_conv, C ABI devis_dcn_im2col / devis_dcn_col2im)
+against fixtures produced by torchvision.ops.deform_conv2d on CPU (the operator the reference's mask head calls,
+deformable_segmentation.py:265) and by the reference's own ModulatedDeformableConv2d / MaskHeadConv modules.
+
+Tolerances (normalised max error): float64 1e-12; float32 forward 1e-5, gradients 1e-4 (the north-star's op tolerances;
+the float32 figures include the cuBLAS GEMM with the weights, run with TF32 off).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, nmax
+
+pytestmark = pytest.mark.gpu
+
+DCN_CASES = ["dcn_k3_mask", "dcn_k3_c24", "dcn_k3_c40", "dcn_stride2_dil2_nomask", "dcn_k1", "dcn_c33"]
+GRAD_KEYS = (("x", "gx"), ("offset", "goffset"), ("weight", "gweight"), ("bias", "gbias"), ("mask", "gmask"))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _run(g, dtype, channels_last=False):
+    from devis_b200.deform_conv import deform_conv2d
+    t = lambda k: torch.from_numpy(g[k]).to("cuda", dtype)
+    st, pd, dl, use_mask = [int(v) for v in g["cfg"]]
+    names = ["x", "offset", "weight", "bias"] + (["mask"] if use_mask else [])
+    leaves = [t(k).clone() for k in names]
+    if channels_last:
+        leaves[0] = leaves[0].contiguous(memory_format=torch.channels_last)
+    leaves = [x.requires_grad_(True) for x in leaves]
+    out = deform_conv2d(leaves[0], leaves[1], leaves[2], leaves[3], stride=st, padding=pd, dilation=dl,
+                        mask=leaves[4] if use_mask else None)
+    out.backward(t("gout"))
+    return out.detach(), dict(zip(names, [x.grad for x in leaves]))
+
+
+@pytest.mark.parametrize("name", DCN_CASES)
+def test_fp64_matches_torchvision_fixture(name):
+    from devis_b200 import _lib
+    g = load_golden(name)
+    before = _lib.launch_count()
+    out, grads = _run(g, torch.float64)
+    assert _lib.launch_count() >= before + 2, "the CUDA kernels were not launched"
+    assert out.shape == g["out"].shape
+    assert nmax(out.cpu().numpy(), g["out"]) < 1e-12
+    for k, key in GRAD_KEYS:
+        if k in grads:
+            assert nmax(grads[k].cpu().numpy(), g[key]) < 1e-12, k
+
+
+@pytest.mark.parametrize("name", DCN_CASES)
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fp32_within_tolerance(name, channels_last):
+    g = load_golden(name)
+    out, grads = _run(g, torch.float32, channels_last)
+    assert nmax(out.cpu().numpy(), g["out"]) < 1e-5
+    for k, key in GRAD_KEYS:
+        if k in grads:
+            assert nmax(grads[k].cpu().numpy(), g[key]) < 1e-4, k
+
+
+def test_half_inputs_are_computed_in_float32_and_cast_back():
+    g = load_golden("dcn_k3_c24")
+    from devis_b200.deform_conv import deform_conv2d
+    t = lambda k: torch.from_numpy(g[k]).to("cuda", torch.bfloat16)
+    out = deform_conv2d(t("x"), t("offset"), t("weight"), t("bias"), padding=1, mask=t("mask"))
+    assert out.dtype == torch.bfloat16
+    want = deform_conv2d(t("x").float(), t("offset").float(), t("weight").float(), t("bias").float(), padding=1,
+                         mask=t("mask").float())
+    assert nmax(out.float().cpu().numpy(), want.cpu().numpy()) < 1e-2
+
+
+def test_matches_installed_torchvision_cuda_op_at_mask_head_shape():
+    """same inputs through torchvision's CUDA operator (third-party baseline) at one real mask-head layer shape:
+    136 -> 64 channels at 23x40, a handful of instances"""
+    tv = pytest.importorskip("torchvision.ops")
+    from devis_b200.deform_conv import deform_conv2d
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    rn = lambda *s: torch.randn(*s, generator=gen, device="cuda")
+    n, cin, cout, h, w = 6, 136, 64, 23, 40
+    x, wt, b = rn(n, cin, h, w), rn(cout, cin, 3, 3) / 35, rn(cout)
+    off, m = 2 * rn(n, 18, h, w), 2 * torch.sigmoid(rn(n, 9, h, w))
+    gout = rn(n, cout, h, w)
+    res = []
+    for fn in (deform_conv2d, tv.deform_conv2d):
+        leaves = [t.clone().requires_grad_(True) for t in (x, off, wt, b, m)]
+        try:
+            out = fn(leaves[0], leaves[1], leaves[2], leaves[3], padding=1, mask=leaves[4])
+        except (RuntimeError, NotImplementedError) as exc:      # torchvision built without its CUDA ops
+            pytest.skip(f"torchvision CUDA deform_conv2d unavailable: {exc}")
+        out.backward(gout)
+        res.append([out.detach()] + [t.grad for t in leaves])
+    for name, a, c in zip(("out", "gx", "goffset", "gweight", "gbias", "gmask"), *res):
+        assert nmax(a.cpu().numpy(), c.cpu().numpy()) < (1e-5 if name == "out" else 1e-4), name
+
+
+def _load_sd(module, g, dtype):
+    sd = {k[3:]: torch.from_numpy(v).to(dtype) for k, v in g.items() if k.startswith("sd.")}
+    module.load_state_dict(sd, strict=True)
+    return module.to("cuda", dtype)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 1e-4)])
+def test_modulated_layer_matches_reference_module(dtype, tol):
+    """reference ModulatedDeformableConv2d (deformable_segmentation.py:244-267): its state dict loads unchanged;
+    output, input gradient and every parameter gradient"""
+    from devis_b200.deformable_segmentation import ModulatedDeformableConv2d
+    g = load_golden("dcn_mod_layer")
+    layer = _load_sd(ModulatedDeformableConv2d(12, 8, 3, padding=1, bias=True), g, dtype)
+    x = torch.from_numpy(g["x"]).to("cuda", dtype).requires_grad_(True)
+    y = layer(x)
+    y.backward(torch.from_numpy(g["gout"]).to("cuda", dtype))
+    assert nmax(y.detach().cpu().numpy(), g["out"]) < tol
+    assert nmax(x.grad.cpu().numpy(), g["gx"]) < tol
+    for k, p in layer.named_parameters():
+        assert nmax(p.grad.cpu().numpy(), g["pg." + k]) < tol, k
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
+def test_mask_head_matches_reference_module(dtype, tol):
+    """reference MaskHeadConv (deformable_segmentation.py:323-380) with deformable layers: five stacked modulated
+    deformable convolutions + GroupNorm + the FPN adapters"""
+    from devis_b200.deformable_segmentation import MaskHeadConv
+    g = load_golden("dcn_mask_head")
+    dim, nheads, n_inst, *fpn_dims = [int(v) for v in g["cfg"]]
+    head = _load_sd(MaskHeadConv(dim, fpn_dims, nheads, True, ["/32", "/16"], 2), g, dtype)
+    feats = [torch.from_numpy(g[f"feat{i}"]).to("cuda", dtype).requires_grad_(True) for i in range(3)]
+    att = [torch.from_numpy(g[f"att{i}"]).to("cuda", dtype) for i in range(2)]
+    expand = lambda t, n: t.unsqueeze(1).repeat(1, int(n), 1, 1, 1).flatten(0, 1)
+    y = head(feats, att, n_inst, expand)
+    y.backward(torch.from_numpy(g["gout"]).to("cuda", dtype))
+    assert nmax(y.detach().cpu().numpy(), g["out"]) < tol
+    for i, f in enumerate(feats):
+        assert nmax(f.grad.cpu().numpy(), g[f"gfeat{i}"]) < tol, i
+
+
+def test_error_behaviour_and_empty_batch():
+    from devis_b200.deform_conv import deform_conv2d
+    x = torch.randn(1, 8, 5, 5, device="cuda")
+    w = torch.randn(4, 8, 3, 3, device="cuda")
+    off = torch.zeros(1, 18, 5, 5, device="cuda")
+    with pytest.raises(RuntimeError):
+        deform_conv2d(x.cpu(), off.cpu(), w.cpu(), padding=1)                    # no CPU path
+    with pytest.raises(RuntimeError):
+        deform_conv2d(x, off[:, :10], w, padding=1)                              # wrong offset channels
+    with pytest.raises(RuntimeError):
+        deform_conv2d(x, off, w[:, :4], padding=1)                               # groups = 2
+    with pytest.raises(RuntimeError):
+        deform_conv2d(x, off, w, padding=1, mask=torch.ones(1, 9, 4, 5, device="cuda"))
+    # zero offsets and no mask: a plain convolution
+    out = deform_conv2d(x, off, w, padding=1)
+    assert nmax(out.cpu().numpy(), torch.nn.functional.conv2d(x, w, padding=1).cpu().numpy()) < 1e-5
+    empty = deform_conv2d(x[:0], off[:0], w, padding=1)
+    assert empty.shape == (0, 4, 5, 5)

@@ -96,3 +96,42 @@ def test_temporal_tables_match_reference_transformer():
     assert np.array_equal(torch.stack(offs).numpy(), g["temporal_offsets"])
     tl = temporal_torch.temporal_level_start_index(torch.from_numpy(g["tshapes"]))
     assert np.array_equal(tl.numpy(), g["tlsi"])
+
+
+DCN_CASES = ["dcn_k3_mask", "dcn_k3_c24", "dcn_k3_c40", "dcn_stride2_dil2_nomask", "dcn_k1", "dcn_c33"]
+
+
+def _dcn_run(fn, g, dtype=torch.float64):
+    t = lambda k: torch.from_numpy(g[k]).to(dtype)
+    st, pd, dl, use_mask = [int(v) for v in g["cfg"]]
+    names = ["x", "offset", "weight", "bias"] + (["mask"] if use_mask else [])
+    leaves = [t(k).clone().requires_grad_(True) for k in names]
+    out = fn(leaves[0], leaves[1], leaves[2], leaves[3], stride=(st, st), padding=(pd, pd), dilation=(dl, dl),
+             mask=leaves[4] if use_mask else None)
+    out.backward(t("gout"))
+    return out.detach(), dict(zip(names, [x.grad for x in leaves]))
+
+
+@pytest.mark.parametrize("name", DCN_CASES)
+def test_deform_conv_restatement_matches_torchvision_fixtures(name):
+    """oracle/deform_conv_torch.py against outputs of torchvision.ops.deform_conv2d (CPU, float64) -- the operator the
+    reference's mask head calls (deformable_segmentation.py:265) -- forward and every gradient"""
+    from oracle import deform_conv_torch
+    g = load_golden(name)
+    out, grads = _dcn_run(deform_conv_torch.deform_conv2d_torch, g)
+    assert nmax(out.numpy(), g["out"]) < 1e-13
+    for k, key in (("x", "gx"), ("offset", "goffset"), ("weight", "gweight"), ("bias", "gbias"), ("mask", "gmask")):
+        if k in grads:
+            assert nmax(grads[k].numpy(), g[key]) < 1e-12, k
+
+
+def test_deform_conv_restatement_matches_installed_torchvision_directly():
+    """same pin without the fixtures: the torchvision in this image, random problem, float64"""
+    tv = pytest.importorskip("torchvision.ops")
+    from oracle import deform_conv_torch
+    g = load_golden("dcn_k3_mask")
+    a, ga = _dcn_run(deform_conv_torch.deform_conv2d_torch, g)
+    b, gb = _dcn_run(tv.deform_conv2d, g)
+    assert nmax(a.numpy(), b.numpy()) < 1e-13
+    for k in ga:
+        assert nmax(ga[k].numpy(), gb[k].numpy()) < 1e-12
