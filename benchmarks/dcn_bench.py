@@ -67,11 +67,18 @@ def main():
         gout = rn(n, cout, h, w)
         row = {"layer": name, "instances": n, "cin": cin, "cout": cout, "hw": [h, w]}
 
+        leaf_sets = {}
+
         def step(fn, xin, backward):
-            leaves = [t.detach().requires_grad_(backward) for t in (xin, off, wt, b, m)]
+            key = (xin.data_ptr(), backward)     # stable leaves, like module parameters (the packed-weight cache hits)
+            if key not in leaf_sets:
+                leaf_sets[key] = [t.detach().requires_grad_(backward) for t in (xin, off, wt, b, m)]
+            leaves = leaf_sets[key]
             out = fn(leaves[0], leaves[1], leaves[2], leaves[3], padding=1, mask=leaves[4])
             if backward:
                 out.backward(gout)
+                for t in leaves:
+                    t.grad = None
 
         row["ours_fwd_us"] = _time(lambda: step(deform_conv2d, x, False), args.iters)
         row["ours_fwd_bwd_us"] = _time(lambda: step(deform_conv2d, x, True), args.iters)
@@ -96,6 +103,22 @@ def main():
         row["col2im_kernel_us"] = _time(lambda: _lib.check(lib.devis_dcn_col2im(
             x.data_ptr(), off.data_ptr(), m.data_ptr(), gcols.data_ptr(), gx.data_ptr(), goff.data_ptr(), gm.data_ptr(),
             *dims, _lib.F32, st)), args.iters)
+        # fused gather + contraction kernels (layers they serve), same way
+        if lib.devis_dcn_fused_lanes(cin, cout, _lib.F32):
+            packed = torch.empty(int(lib.devis_dcn_packed_weight_elems(cin, cout, 3, 3)), device="cuda")
+            _lib.check(lib.devis_dcn_pack_weight(wt.data_ptr(), packed.data_ptr(), cin, cout, 3, 3, st))
+            out = torch.empty(n, h, w, cout, device="cuda")
+            gl = gout.permute(0, 2, 3, 1).contiguous()
+            row["fused_fwd_kernel_us"] = _time(lambda: _lib.check(lib.devis_dcn_fused_forward(
+                x.data_ptr(), off.data_ptr(), m.data_ptr(), packed.data_ptr(), b.data_ptr(), out.data_ptr(), *dims, cout,
+                st)), args.iters)
+            row["fused_bwd_kernel_us"] = _time(lambda: _lib.check(lib.devis_dcn_fused_backward(
+                x.data_ptr(), off.data_ptr(), m.data_ptr(), packed.data_ptr(), gl.data_ptr(), gx.data_ptr(),
+                goff.data_ptr(), gm.data_ptr(), *dims, cout, st)), args.iters)
+            fb = 4 * (x.numel() + off.numel() + m.numel() + out.numel())
+            row["fused_fwd_GBps"] = fb / row["fused_fwd_kernel_us"] / 1e3
+            bb = 4 * (x.numel() + off.numel() + m.numel() + gl.numel() + gx.numel() + goff.numel() + gm.numel())
+            row["fused_bwd_GBps"] = bb / row["fused_bwd_kernel_us"] / 1e3
         # algorithmic bytes of the gather: input + offset + mask read once, columns written once
         fwd_bytes = 4 * (x.numel() + off.numel() + m.numel() + cols.numel())
         row["im2col_GBps"] = fwd_bytes / row["im2col_kernel_us"] / 1e3

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def _deps():
-    deps = [os.path.join(HERE, "..", "include", "devis_msda.h")]
+    deps = [os.path.join(HERE, "..", "include", h) for h in ("devis_msda.h", "devis_deform_conv.h")]
     for name in os.listdir(CSRC):
         if name.endswith((".cu", ".cuh", ".h")):
             deps.append(os.path.join(CSRC, name))

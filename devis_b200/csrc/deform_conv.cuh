@@ -243,4 +243,215 @@ __global__ void __launch_bounds__(256) dcn_col2im_kernel(const T *__restrict__ i
     }
 }
 
+// =====================================================================================================================
+// Fused kernels: gather + contraction with the convolution weights in one pass, the column matrix is never written.
+//
+// For the high-resolution layers of the mask head (few output channels: 72->32 at 45x80, 32->16 and 16->1 at 90x160)
+// the column matrix is 9x the input and the GEMM is a thin one, so im2col + cuBLAS spends its time writing and
+// re-reading columns (995 MB per direction for 60 instances at 90x160).  Here a group of G lanes owns one output pixel;
+// a lane owns the channel pieces c = j, j+G, ... (4 channels each), interpolates them for kernel position k and
+// immediately multiplies by the weights of (k, piece), accumulating COUT partial outputs in registers; after the 9
+// positions the partials are combined over the group with a reduce-scatter butterfly and each lane stores COUT/G
+// outputs.  HBM traffic = input + offsets + mask + output, once each.
+//
+// PACKED WEIGHTS (devis_dcn_pack_weight): wp[((k * nblk + b) * COUT + co) * G + jj] is a float4 holding
+// weight[co][(b*G + jj)*4 + 0..3][ky][kx] (zero beyond C), nblk = ceil(C / (4*G)).  For a fixed (k, b, co) the G lanes
+// of a group read 16*G contiguous bytes and all groups of a warp read the same bytes (one L1 wavefront, broadcast).
+// =====================================================================================================================
+__global__ void dcn_pack_weight_kernel(const float *__restrict__ w /* (Cout, C, kh, kw) */, float *__restrict__ wp,
+                                       int cout, int C, int K, int G, int nblk)
+{
+    const long long total = (long long)K * nblk * cout * G * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i & 3);
+        long long r = i >> 2;
+        const int jj = (int)(r % G);
+        r /= G;
+        const int co = (int)(r % cout);
+        r /= cout;
+        const int b = (int)(r % nblk);
+        const int k = (int)(r / nblk);
+        const int c = (b * G + jj) * 4 + e;
+        wp[i] = c < C ? w[((long long)co * C + c) * K + k] : 0.f;
+    }
+}
+
+struct DcnPixelId {
+    int n, ho, wo;
+};
+
+__device__ __forceinline__ DcnPixelId dcn_pixel_id(long long pixel, const DcnDims &d)
+{
+    DcnPixelId p;
+    p.wo = (int)(pixel % d.Wo);
+    const long long r = pixel / d.Wo;
+    p.ho = (int)(r % d.Ho);
+    p.n = (int)(r / d.Ho);
+    return p;
+}
+
+// sum of v[0..N) over the G lanes of a group.  N >= G: reduce-scatter, lane j ends with the totals of
+// v[j*N/G .. (j+1)*N/G) in v[0 .. N/G).  N < G: every lane ends with all totals.
+template <int N, int G>
+__device__ __forceinline__ void dcn_group_sum(float (&v)[N], int j)
+{
+    if (N >= G) {
+        int half = N / 2;
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1, half >>= 1) {
+            const bool up = (j & o) != 0;
+#pragma unroll
+            for (int i = 0; i < N / 2; ++i) {
+                if (i < half) {
+                    const float send = up ? v[i] : v[i + half];
+                    const float keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o, G);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o, G);
+    }
+}
+
+template <int COUT, int G>
+__global__ void __launch_bounds__(256) dcn_fused_fwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+                                                            const float *__restrict__ mask, const float4 *__restrict__ wp,
+                                                            const float *__restrict__ bias, float *__restrict__ out,
+                                                            DcnDims d, long long n_pixels)
+{
+    const int j = threadIdx.x % G;
+    long long pixel = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool live = pixel < n_pixels;
+    if (!live) pixel = n_pixels - 1;   // keep whole warps in the shuffles; dead groups store nothing
+    const DcnPixelId p = dcn_pixel_id(pixel, d);
+    const int K = d.kh * d.kw, C4 = d.C / 4, nblk = (C4 + G - 1) / G;
+    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)p.n * d.H * d.W * d.C);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+    DcnTapId id;
+    id.n = p.n, id.ho = p.ho, id.wo = p.wo, id.pixel = pixel;
+    for (int k = 0; k < K; ++k) {
+        id.k = k;
+        float h, w, m;
+        dcn_sample_point(offset, mask, id, d, h, w, m);
+        const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
+        if (!t.inside) continue;       // uniform per group; the shuffles come after the loop
+        const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
+        const float4 *r0 = img + (long long)t.row[0] * C4, *r1 = img + (long long)t.row[1] * C4;
+        const float4 *r2 = img + (long long)t.row[2] * C4, *r3 = img + (long long)t.row[3] * C4;
+        for (int b = 0; b < nblk; ++b) {
+            const int c = b * G + j;
+            if (c >= C4) break;
+            const float4 a = __ldg(r0 + c), bb = __ldg(r1 + c), e = __ldg(r2 + c), f = __ldg(r3 + c);
+            float4 v;
+            v.x = f0 * a.x + f1 * bb.x + f2 * e.x + f3 * f.x;
+            v.y = f0 * a.y + f1 * bb.y + f2 * e.y + f3 * f.y;
+            v.z = f0 * a.z + f1 * bb.z + f2 * e.z + f3 * f.z;
+            v.w = f0 * a.w + f1 * bb.w + f2 * e.w + f3 * f.w;
+            const float4 *wk = wp + ((long long)(k * nblk + b) * COUT) * G + j;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float4 w4 = __ldg(wk + co * G);
+                acc[co] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, acc[co]))));
+            }
+        }
+    }
+    dcn_group_sum<COUT, G>(acc, j);
+    if (!live) return;
+    float *o = out + pixel * COUT;
+    if (COUT >= G) {
+        constexpr int PER = COUT >= G ? COUT / G : 1;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) o[j * PER + i] = acc[i] + (bias ? bias[j * PER + i] : 0.f);
+    } else if (j < COUT) {
+        float mine = acc[0];
+#pragma unroll
+        for (int i = 1; i < COUT; ++i) mine = j == i ? acc[i] : mine;
+        o[j] = mine + (bias ? bias[j] : 0.f);
+    }
+}
+
+// Backward of the fused form with respect to the data: grad_cols is never materialised.  Per (pixel, k) the lane
+// forms its slice of the column gradient on the fly, gc[c] = sum_co grad_out[pixel][co] * weight[co][c][k], and uses it
+// exactly like dcn_col2im_kernel uses grad_cols: corner dot products -> grad_offset / grad_mask, 16-byte vector
+// reductions -> grad_input.  The weight gradient (cols^T x grad_out) is computed by the caller from recomputed columns.
+template <int COUT, int G>
+__global__ void __launch_bounds__(256) dcn_fused_bwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+                                                            const float *__restrict__ mask, const float4 *__restrict__ wp,
+                                                            const float *__restrict__ grad_out /* (pixels, COUT) */,
+                                                            float *__restrict__ grad_input, float *__restrict__ grad_offset,
+                                                            float *__restrict__ grad_mask, DcnDims d, long long n_pixels)
+{
+    const int j = threadIdx.x % G;
+    long long pixel = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool live = pixel < n_pixels;
+    if (!live) pixel = n_pixels - 1;
+    const DcnPixelId p = dcn_pixel_id(pixel, d);
+    const int K = d.kh * d.kw, C4 = d.C / 4, nblk = (C4 + G - 1) / G;
+    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)p.n * d.H * d.W * d.C);
+    float *gimg = grad_input ? grad_input + (long long)p.n * d.H * d.W * d.C : nullptr;
+    float g[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) g[co] = __ldg(grad_out + pixel * COUT + co);
+    DcnTapId id;
+    id.n = p.n, id.ho = p.ho, id.wo = p.wo, id.pixel = pixel;
+    const long long plane = (long long)d.Ho * d.Wo, at = (long long)p.ho * d.Wo + p.wo;
+    for (int k = 0; k < K; ++k) {
+        id.k = k;
+        float h, w, m;
+        dcn_sample_point(offset, mask, id, d, h, w, m);
+        const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
+        float A[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t.inside) {                // uniform per group
+            const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
+            for (int b = 0; b < nblk; ++b) {
+                const int c = b * G + j;
+                if (c >= C4) break;
+                const float4 *wk = wp + ((long long)(k * nblk + b) * COUT) * G + j;
+                float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float4 w4 = __ldg(wk + co * G);
+                    gc.x = fmaf(g[co], w4.x, gc.x);
+                    gc.y = fmaf(g[co], w4.y, gc.y);
+                    gc.z = fmaf(g[co], w4.z, gc.z);
+                    gc.w = fmaf(g[co], w4.w, gc.w);
+                }
+                const float4 a = __ldg(img + (long long)t.row[0] * C4 + c), bb = __ldg(img + (long long)t.row[1] * C4 + c);
+                const float4 e = __ldg(img + (long long)t.row[2] * C4 + c), f = __ldg(img + (long long)t.row[3] * C4 + c);
+                A[0] += gc.x * a.x + gc.y * a.y + gc.z * a.z + gc.w * a.w;
+                A[1] += gc.x * bb.x + gc.y * bb.y + gc.z * bb.z + gc.w * bb.w;
+                A[2] += gc.x * e.x + gc.y * e.y + gc.z * e.z + gc.w * e.w;
+                A[3] += gc.x * f.x + gc.y * f.y + gc.z * f.z + gc.w * f.w;
+                if (live && gimg) {
+                    if (f0 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[0] * C4 + c) * 4, f0 * gc.x, f0 * gc.y, f0 * gc.z, f0 * gc.w);
+                    if (f1 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[1] * C4 + c) * 4, f1 * gc.x, f1 * gc.y, f1 * gc.z, f1 * gc.w);
+                    if (f2 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[2] * C4 + c) * 4, f2 * gc.x, f2 * gc.y, f2 * gc.z, f2 * gc.w);
+                    if (f3 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[3] * C4 + c) * 4, f3 * gc.x, f3 * gc.y, f3 * gc.z, f3 * gc.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) A[i] += __shfl_xor_sync(0xffffffffu, A[i], o, G);
+        }
+        if (live && j == 0) {
+            const float A0 = t.ok[0] ? A[0] : 0.f, A1 = t.ok[1] ? A[1] : 0.f;
+            const float A2 = t.ok[2] ? A[2] : 0.f, A3 = t.ok[3] ? A[3] : 0.f;
+            const float val = t.hh * (t.hw * A0 + t.lw * A1) + t.lh * (t.hw * A2 + t.lw * A3);
+            const float gh = t.hw * (A2 - A0) + t.lw * (A3 - A1);
+            const float gw = t.hh * (A1 - A0) + t.lh * (A3 - A2);
+            grad_offset[((long long)p.n * 2 * K + 2 * k) * plane + at] = t.inside ? m * gh : 0.f;
+            grad_offset[((long long)p.n * 2 * K + 2 * k + 1) * plane + at] = t.inside ? m * gw : 0.f;
+            if (grad_mask) grad_mask[((long long)p.n * K + k) * plane + at] = t.inside ? val : 0.f;
+        }
+    }
+}
+
 }  // namespace devis

@@ -107,4 +107,116 @@ int devis_dcn_col2im(const void *input, const void *offset, const void *mask, co
                     [&](unsigned b) { dcn_col2im_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); });
 }
 
+
+// ---- fused gather + contraction (no column matrix) -------------------------------------------------------------------
+
+static int fused_lanes(int channels, int out_channels, int dtype)
+{
+    if (dtype != DEVIS_MSDA_F32 || channels <= 0 || channels % 4) return 0;
+    switch (out_channels) {
+    case 1: case 2: case 4: case 8: case 16: case 32: case 64: break;
+    default: return 0;
+    }
+    return channels / 4 > 4 ? 8 : 4;
+}
+
+int devis_dcn_fused_lanes(int channels, int out_channels, int dtype) { return fused_lanes(channels, out_channels, dtype); }
+
+size_t devis_dcn_packed_weight_elems(int channels, int out_channels, int kernel_h, int kernel_w)
+{
+    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
+    if (!G || kernel_h <= 0 || kernel_w <= 0) return 0;
+    const int nblk = (channels / 4 + G - 1) / G;
+    return (size_t)kernel_h * kernel_w * nblk * out_channels * G * 4;
+}
+
+int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int out_channels, int kernel_h, int kernel_w,
+                          void *stream)
+{
+    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
+    if (!G) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    if (kernel_h <= 0 || kernel_w <= 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (!weight || !packed) return DEVIS_MSDA_ERR_NULL_POINTER;
+    const int nblk = (channels / 4 + G - 1) / G, K = kernel_h * kernel_w;
+    const long long total = (long long)K * nblk * out_channels * G * 4;
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    dcn_pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float *)weight, (float *)packed, out_channels,
+                                                                    channels, K, G, nblk);
+    return devis_capi_check_launch();
+}
+
+#define DCN_FUSED_CASES(KERNEL, G, ...)                                                      \
+    switch (out_channels) {                                                                  \
+    case 1: KERNEL<1, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
+    case 2: KERNEL<2, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
+    case 4: KERNEL<4, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
+    case 8: KERNEL<8, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
+    case 16: KERNEL<16, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                      \
+    case 32: KERNEL<32, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                      \
+    default: KERNEL<64, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                      \
+    }
+
+int devis_dcn_fused_forward(const void *input, const void *offset, const void *mask, const void *packed_weight,
+                            const void *bias, void *out, int batch, int height, int width, int channels, int out_h,
+                            int out_w, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                            int dil_h, int dil_w, int out_channels, void *stream)
+{
+    const DcnDims d{batch, height, width, channels, out_h, out_w, kernel_h, kernel_w,
+                    stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
+    const int rc = check_dims(d, DEVIS_MSDA_F32);
+    if (rc) return rc;
+    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
+    if (!G) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const long long n_pixels = (long long)batch * out_h * out_w;
+    if (n_pixels == 0) return DEVIS_MSDA_OK;
+    if (!input || !offset || !packed_weight || !out) return DEVIS_MSDA_ERR_NULL_POINTER;
+    const long long nb = (n_pixels * G + 255) / 256;
+    if (nb > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    const unsigned blocks = (unsigned)nb;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
+    const float4 *wp = (const float4 *)packed_weight;
+    const float *bs = (const float *)bias;
+    float *o = (float *)out;
+    if (G == 8) { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 8, in, of, mk, wp, bs, o, d, n_pixels) }
+    else { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 4, in, of, mk, wp, bs, o, d, n_pixels) }
+    return devis_capi_check_launch();
+}
+
+int devis_dcn_fused_backward(const void *input, const void *offset, const void *mask, const void *packed_weight,
+                             const void *grad_out, void *grad_input, void *grad_offset, void *grad_mask, int batch,
+                             int height, int width, int channels, int out_h, int out_w, int kernel_h, int kernel_w,
+                             int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int out_channels,
+                             void *stream)
+{
+    const DcnDims d{batch, height, width, channels, out_h, out_w, kernel_h, kernel_w,
+                    stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
+    const int rc = check_dims(d, DEVIS_MSDA_F32);
+    if (rc) return rc;
+    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
+    if (!G) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const long long n_pixels = (long long)batch * out_h * out_w;
+    if (n_pixels > 0 && (!input || !offset || !packed_weight || !grad_out || !grad_offset || (mask && !grad_mask)))
+        return DEVIS_MSDA_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_input) {
+        const size_t bytes = (size_t)batch * height * width * channels * 4;
+        if (bytes) {
+            const cudaError_t e = cudaMemsetAsync(grad_input, 0, bytes, st);
+            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+        }
+    }
+    if (n_pixels == 0) return DEVIS_MSDA_OK;
+    const long long nb = (n_pixels * G + 255) / 256;
+    if (nb > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    const unsigned blocks = (unsigned)nb;
+    const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
+    const float4 *wp = (const float4 *)packed_weight;
+    const float *go = (const float *)grad_out;
+    float *gi = (float *)grad_input, *gof = (float *)grad_offset, *gm = (float *)grad_mask;
+    if (G == 8) { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 8, in, of, mk, wp, go, gi, gof, gm, d, n_pixels) }
+    else { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 4, in, of, mk, wp, go, gi, gof, gm, d, n_pixels) }
+    return devis_capi_check_launch();
+}
+
 }  // extern "C"

@@ -14,9 +14,19 @@ devis_b200/csrc/deform_conv.cuh); the contractions with ``weight`` are cuBLAS GE
 The input is read channels-last: pass a ``torch.channels_last`` tensor to avoid the layout copy; the result is returned
 as an NCHW view of a channels-last buffer.
 
+Two forms (both hand-written kernels of this library, chosen per layer by ``devis_dcn_fused_lanes``):
+  * fused  -- float32, Cin % 4 == 0, Cout in {1, 2, 4, 8, 16, 32, 64} (the high-resolution half of the mask head): gather
+              and contraction in ONE kernel, the column matrix (9x the input) is never written; backward = one kernel
+              for the data gradients (no grad_cols either) + the weight gradient from columns recomputed in bounded
+              chunks, so nothing of column size is kept between forward and backward;
+  * im2col -- everything else: column matrix + cuBLAS GEMM, as torchvision does.
+``set_fused(False)`` forces the im2col form (A/B tests).
+
 Supported: groups == 1 and offset_groups == 1 (everything DeVIS uses), float32 / float64 (half and bfloat16 are
 computed in float32 like torchvision's autocast wrapper does), CUDA only -- there is no CPU fallback.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -33,6 +43,108 @@ def _ptr(t):
 
 def _out_size(size, k, stride, pad, dil):
     return (size + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+_FUSED = True
+_COLS_CHUNK_BYTES = 256 << 20          # recomputed columns per weight-gradient chunk
+_packed_cache = {}
+
+
+def set_fused(enabled):
+    """enable / disable the fused gather+contraction kernels (default on); returns the previous setting"""
+    global _FUSED
+    old, _FUSED = _FUSED, bool(enabled)
+    return old
+
+
+def _fused_lanes(c, cout, dtype):
+    if not _FUSED or dtype != torch.float32:
+        return 0
+    return int(_lib.load().devis_dcn_fused_lanes(c, cout, _lib.F32))
+
+
+def _packed_weight(weight):
+    """weight (Cout, Cin, kh, kw) in the layout the fused kernels read; cached per tensor object and version"""
+    hit = _packed_cache.get(id(weight))
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    cout, c, kh, kw = weight.shape
+    lib = _lib.load()
+    w = weight.detach()
+    w = w if w.is_contiguous() else w.contiguous()
+    packed = torch.empty(int(lib.devis_dcn_packed_weight_elems(c, cout, kh, kw)), dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(lib.devis_dcn_pack_weight(_ptr(w), _ptr(packed), c, cout, kh, kw, torch.cuda.current_stream().cuda_stream))
+    if len(_packed_cache) >= 64:
+        _packed_cache.clear()
+    _packed_cache[id(weight)] = (weakref.ref(weight), weight._version, packed)
+    return packed
+
+
+class FusedDeformConv2dFunction(Function):
+    """apply(input, offset, weight, bias, mask, stride, padding, dilation) -> (N, Cout, Ho, Wo), fused kernels"""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, bias, mask, stride, padding, dilation):
+        n, c, h, w = input.shape
+        cout, _, kh, kw = weight.shape
+        (sh, sw), (ph, pw), (dh, dw) = stride, padding, dilation
+        ho, wo = _out_size(h, kh, sh, ph, dh), _out_size(w, kw, sw, pw, dw)
+        x = input.permute(0, 2, 3, 1)
+        x = x if x.is_contiguous() else x.contiguous()
+        offset = offset if offset.is_contiguous() else offset.contiguous()
+        if mask is not None:
+            mask = mask if mask.is_contiguous() else mask.contiguous()
+        if bias is not None:
+            bias = bias if bias.is_contiguous() else bias.contiguous()
+        packed = _packed_weight(weight)
+        out = torch.empty((n, ho, wo, cout), dtype=input.dtype, device=input.device)
+        dims = (n, h, w, c, ho, wo, kh, kw, sh, sw, ph, pw, dh, dw)
+        with torch.cuda.device(input.device):
+            _lib.check(_lib.load().devis_dcn_fused_forward(_ptr(x), _ptr(offset), _ptr(mask), _ptr(packed), _ptr(bias),
+                                                           _ptr(out), *dims, cout,
+                                                           torch.cuda.current_stream().cuda_stream))
+        ctx.dims, ctx.cout, ctx.has_bias = dims, cout, bias is not None
+        ctx.save_for_backward(x, offset, mask, packed)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, offset, mask, packed = ctx.saved_tensors
+        n, h, w, c, ho, wo, kh, kw = ctx.dims[:8]
+        cout, k = ctx.cout, kh * kw
+        g = grad_out.permute(0, 2, 3, 1)
+        g = g if g.is_contiguous() else g.contiguous()                    # (N, Ho, Wo, Cout)
+        need_in, need_off, need_w, need_b, need_m = ctx.needs_input_grad[:5]
+        grad_w = grad_b = grad_in = grad_off = grad_m = None
+        lib = _lib.load()
+        stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(x.device):
+            if need_in or need_off or (need_m and mask is not None):
+                gx = torch.empty_like(x) if need_in else None
+                grad_off = torch.empty_like(offset)
+                grad_m = torch.empty_like(mask) if mask is not None else None
+                _lib.check(lib.devis_dcn_fused_backward(_ptr(x), _ptr(offset), _ptr(mask), _ptr(packed), _ptr(g), _ptr(gx),
+                                                        _ptr(grad_off), _ptr(grad_m), *ctx.dims, cout, stream))
+                grad_in = gx.permute(0, 3, 1, 2) if need_in else None
+            if need_w:
+                # cols^T x grad_out from columns recomputed a bounded chunk of the batch at a time
+                per = max(1, min(n, _COLS_CHUNK_BYTES // max(1, ho * wo * k * c * 4)))
+                cols = torch.empty((per * ho * wo, k * c), dtype=x.dtype, device=x.device)
+                gw2 = torch.zeros((cout, k * c), dtype=x.dtype, device=x.device)
+                g2 = g.view(n * ho * wo, cout)
+                for n0 in range(0, n, per):
+                    n1 = min(n, n0 + per)
+                    rows = (n1 - n0) * ho * wo
+                    _lib.check(lib.devis_dcn_im2col(_ptr(x[n0:n1]), _ptr(offset[n0:n1]),
+                                                    _ptr(mask[n0:n1]) if mask is not None else None, _ptr(cols),
+                                                    n1 - n0, *ctx.dims[1:], _DTYPES[x.dtype], stream))
+                    gw2.addmm_(g2[n0 * ho * wo:n1 * ho * wo].t(), cols[:rows])
+                grad_w = gw2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
+        if need_b and ctx.has_bias:
+            grad_b = g.sum((0, 1, 2))
+        return grad_in, grad_off, grad_w, grad_b, grad_m, None, None, None
 
 
 class DeformConv2dFunction(Function):
@@ -119,5 +231,6 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     elif out_dtype not in _DTYPES:
         raise RuntimeError(f'"deform_conv2d" not implemented for \'{out_dtype}\'')
     same = lambda t: None if t is None else (t if t.dtype == input.dtype else t.to(input.dtype))
-    out = DeformConv2dFunction.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
+    fn = FusedDeformConv2dFunction if n > 0 and _fused_lanes(c, cout, input.dtype) else DeformConv2dFunction
+    out = fn.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
     return out if out.dtype == out_dtype else out.to(out_dtype)

@@ -402,6 +402,14 @@ def make_dcn_fixtures(seg):
         "dcn_stride2_dil2_nomask": (2, 6, 4, 9, 8, 3, 2, 2, 2, False, 1.0),
         "dcn_k1": (1, 3, 2, 5, 5, 1, 1, 0, 1, True, 0.7),
         "dcn_c33": (1, 33, 3, 4, 5, 3, 1, 1, 1, True, 1.0),             # scalar path, 32 lanes
+        # layers the fused gather+contraction kernels serve (Cout in {1,2,4,8,16,32,64}, Cin % 4 == 0)
+        "dcn_fused_c32_o16": (2, 32, 16, 6, 7, 3, 1, 1, 1, True, 1.5),  # the 90x160 layer of the mask head, 8 lanes
+        "dcn_fused_c72_o32": (1, 72, 32, 5, 6, 3, 1, 1, 1, True, 3.0),  # ragged last channel block, taps leaving the map
+        "dcn_fused_c16_o1": (2, 16, 1, 6, 5, 3, 1, 1, 1, True, 1.0),    # out_lay: 4 lanes, fewer outputs than lanes
+        "dcn_fused_c8_o4_s2": (2, 8, 4, 9, 8, 3, 2, 2, 2, False, 1.0),  # stride / dilation, no mask
+        "dcn_fused_c40_o64": (1, 40, 64, 4, 5, 3, 1, 1, 1, True, 1.0),
+        "dcn_fused_c20_o2": (1, 20, 2, 5, 4, 3, 1, 1, 1, False, 2.0),
+        "dcn_fused_c136_o8_k1": (1, 136, 8, 4, 4, 1, 1, 0, 1, True, 0.8),
     }
     for name, (n, cin, cout, h, w, k, st, pd, dl, use_mask, osc) in cases.items():
         ho = (h + 2 * pd - (dl * (k - 1) + 1)) // st + 1

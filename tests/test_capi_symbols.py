@@ -63,6 +63,18 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.devis_dcn_im2col(null, null, null, null, *dims, 0, null) == -1
     assert lib.devis_dcn_col2im(null, null, null, null, null, null, null, *dims, 0, null) == -1
     assert lib.devis_dcn_im2col(null, null, null, null, *((0,) + dims[1:]), 0, null) == 0
+    # fused form: which layers it serves, packed-weight size, validation order
+    assert lib.devis_dcn_fused_lanes(32, 16, 0) == 8 and lib.devis_dcn_fused_lanes(16, 1, 0) == 4
+    assert lib.devis_dcn_fused_lanes(72, 32, 0) == 8 and lib.devis_dcn_fused_lanes(264, 128, 0) == 0
+    assert lib.devis_dcn_fused_lanes(30, 16, 0) == 0 and lib.devis_dcn_fused_lanes(32, 16, 1) == 0
+    assert lib.devis_dcn_packed_weight_elems(72, 32, 3, 3) == 9 * 3 * 32 * 8 * 4
+    assert lib.devis_dcn_packed_weight_elems(72, 5, 3, 3) == 0
+    assert lib.devis_dcn_pack_weight(null, null, 72, 5, 3, 3, null) == -8
+    assert lib.devis_dcn_pack_weight(null, null, 72, 32, 3, 3, null) == -1
+    assert lib.devis_dcn_fused_forward(null, null, null, null, null, null, *dims, 16, null) == -1
+    assert lib.devis_dcn_fused_forward(null, null, null, null, null, null, *dims, 5, null) == -8
+    assert lib.devis_dcn_fused_backward(null, null, null, null, null, null, null, null, *dims, 16, null) == -1
+    assert lib.devis_dcn_fused_forward(null, null, null, null, null, null, *((0,) + dims[1:]), 16, null) == 0
     # empty problems are fine with null pointers and launch nothing
     before = lib.devis_msda_launch_count()
     assert lib.devis_msda_forward(null, null, null, null, null, null, 0, 4, 2, 32, 1, 0, 1, 64, 0, null) == 0
