@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--json", default=None)
     ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--layers", default=None, help="comma-separated subset of layer names (e.g. lay5,out_lay)")
+    ap.add_argument("--no-torchvision", action="store_true")
     args = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = args.tf32
     from devis_b200 import _lib
@@ -60,7 +62,11 @@ def main():
     rn = lambda *s: torch.randn(*s, generator=gen, device="cuda")
     n = args.instances
     rows, tot = [], {}
+    if args.no_torchvision:
+        tv_deform_conv2d = None
     for name, cin, cout, h, w in LAYERS:
+        if args.layers and name not in args.layers.split(","):
+            continue
         x = rn(n, cin, h, w).contiguous(memory_format=torch.channels_last)
         wt, b = rn(cout, cin, 3, 3) / (3 * cin ** 0.5), rn(cout)
         off, m = 1.5 * rn(n, 18, h, w), 2 * torch.sigmoid(rn(n, 9, h, w))

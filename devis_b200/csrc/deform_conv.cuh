@@ -79,24 +79,23 @@ __device__ __forceinline__ DcnTap<T> dcn_tap(T h, T w, int H, int W)
     return t;
 }
 
-// tap index -> (n, k, ho, wo) with wo fastest: the groups of a warp work on neighbouring output pixels for the same
-// kernel position, so their offset / mask reads are coalesced and their gathers share a neighbourhood of the input
+// A tap is addressed by the launch grid: blockIdx.z (+ n_base) = batch item, blockIdx.y = kernel position, and the
+// x dimension runs over the output plane with wo fastest: the groups of a warp work on neighbouring output pixels for
+// the same kernel position, so their offset / mask reads are coalesced and their gathers share a neighbourhood of the
+// input.  (32-bit arithmetic only: a 64-bit division per index component cost more than the gather itself.)
 struct DcnTapId {
     int n, k, ho, wo;
     long long pixel;   // (n * Ho + ho) * Wo + wo
 };
 
-__device__ __forceinline__ DcnTapId dcn_tap_id(long long tap, const DcnDims &d)
+__device__ __forceinline__ DcnTapId dcn_tap_id(int plane_pixel, int n, int k, const DcnDims &d)
 {
     DcnTapId id;
-    const int K = d.kh * d.kw;
-    id.wo = (int)(tap % d.Wo);
-    long long r = tap / d.Wo;
-    id.ho = (int)(r % d.Ho);
-    r /= d.Ho;
-    id.k = (int)(r % K);
-    id.n = (int)(r / K);
-    id.pixel = ((long long)id.n * d.Ho + id.ho) * d.Wo + id.wo;
+    id.n = n;
+    id.k = k;
+    id.ho = plane_pixel / d.Wo;
+    id.wo = plane_pixel - id.ho * d.Wo;
+    id.pixel = (long long)n * d.Ho * d.Wo + plane_pixel;
     return id;
 }
 
@@ -122,12 +121,12 @@ __device__ __forceinline__ void dcn_sample_point(const T *offset, const T *mask,
 template <typename T, int V, int G>
 __global__ void __launch_bounds__(256) dcn_im2col_kernel(const T *__restrict__ input, const T *__restrict__ offset,
                                                          const T *__restrict__ mask, T *__restrict__ cols, DcnDims d,
-                                                         long long n_taps)
+                                                         int n_base)
 {
     const int j = threadIdx.x % G;
-    const long long tap = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (tap >= n_taps) return;
-    const DcnTapId id = dcn_tap_id(tap, d);
+    const int pp = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+    if (pp >= d.Ho * d.Wo) return;
+    const DcnTapId id = dcn_tap_id(pp, n_base + (int)blockIdx.z, (int)blockIdx.y, d);
     T h, w, m;
     dcn_sample_point(offset, mask, id, d, h, w, m);
     const DcnTap<T> t = dcn_tap(h, w, d.H, d.W);
@@ -166,13 +165,13 @@ template <typename T, int V, int G>
 __global__ void __launch_bounds__(256) dcn_col2im_kernel(const T *__restrict__ input, const T *__restrict__ offset,
                                                          const T *__restrict__ mask, const T *__restrict__ grad_cols,
                                                          T *__restrict__ grad_input, T *__restrict__ grad_offset,
-                                                         T *__restrict__ grad_mask, DcnDims d, long long n_taps)
+                                                         T *__restrict__ grad_mask, DcnDims d, int n_base)
 {
     const int j = threadIdx.x % G;
-    long long tap = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool live = tap < n_taps;
-    if (!live) tap = n_taps - 1;   // keep the whole warp in the shuffles below; results of dead groups are dropped
-    const DcnTapId id = dcn_tap_id(tap, d);
+    int pp = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+    const bool live = pp < d.Ho * d.Wo;
+    if (!live) pp = d.Ho * d.Wo - 1;   // keep the whole warp in the shuffles below; results of dead groups are dropped
+    const DcnTapId id = dcn_tap_id(pp, n_base + (int)blockIdx.z, (int)blockIdx.y, d);
     T h, w, m;
     dcn_sample_point(offset, mask, id, d, h, w, m);
     const DcnTap<T> t = dcn_tap(h, w, d.H, d.W);
@@ -276,20 +275,6 @@ __global__ void dcn_pack_weight_kernel(const float *__restrict__ w /* (Cout, C, 
     }
 }
 
-struct DcnPixelId {
-    int n, ho, wo;
-};
-
-__device__ __forceinline__ DcnPixelId dcn_pixel_id(long long pixel, const DcnDims &d)
-{
-    DcnPixelId p;
-    p.wo = (int)(pixel % d.Wo);
-    const long long r = pixel / d.Wo;
-    p.ho = (int)(r % d.Ho);
-    p.n = (int)(r / d.Ho);
-    return p;
-}
-
 // sum of v[0..N) over the G lanes of a group.  N >= G: reduce-scatter, lane j ends with the totals of
 // v[j*N/G .. (j+1)*N/G) in v[0 .. N/G).  N < G: every lane ends with all totals.
 template <int N, int G>
@@ -317,62 +302,126 @@ __device__ __forceinline__ void dcn_group_sum(float (&v)[N], int j)
     }
 }
 
-template <int COUT, int G>
-__global__ void __launch_bounds__(256) dcn_fused_fwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+// Work split of the fused kernels.  A block of 32*WARPS threads owns a tile of WARPS rows x TW = (32/G)*PPG columns of
+// one output plane (blockIdx.z + n_base = batch item): warp w works on tile row w, a group of G lanes on PPG pixels next
+// to each other -- the weights fetched for a (kernel position, channel block) are used for PPG pixels, and the tile's
+// gathers stay in one neighbourhood of the input (L1 hits).  Pixels beyond the plane are computed on clamped
+// coordinates (their lanes must take part in the group shuffles) and never stored.
+template <int G, int PPG>
+struct DcnTile {
+    int j, n, ho, wo[PPG];
+    bool row_live, live[PPG];
+    long long at[PPG];     // ho * Wo + wo on clamped coordinates
+    __device__ __forceinline__ DcnTile(const DcnDims &d, int n_base)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        j = lane % G;
+        n = n_base + (int)blockIdx.z;
+        const int h = (int)blockIdx.y * (int)(blockDim.x >> 5) + warp;
+        row_live = h < d.Ho;
+        ho = min(h, d.Ho - 1);
+#pragma unroll
+        for (int i = 0; i < PPG; ++i) {
+            const int w = ((int)blockIdx.x * (32 / G) + lane / G) * PPG + i;
+            live[i] = row_live && w < d.Wo;
+            wo[i] = min(w, d.Wo - 1);
+            at[i] = (long long)ho * d.Wo + wo[i];
+        }
+    }
+};
+
+struct DcnPoint {
+    float oh, ow, m;
+};
+
+__device__ __forceinline__ DcnPoint dcn_load_point(const float *offset_n, const float *mask_n, int k, long long plane,
+                                                   long long at)
+{
+    DcnPoint p;
+    p.oh = __ldg(offset_n + (2 * k) * plane + at);
+    p.ow = __ldg(offset_n + (2 * k + 1) * plane + at);
+    p.m = mask_n ? __ldg(mask_n + k * plane + at) : 1.f;
+    return p;
+}
+
+template <int COUT, int G, int PPG>
+__global__ void __launch_bounds__(256, 2) dcn_fused_fwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
                                                             const float *__restrict__ mask, const float4 *__restrict__ wp,
                                                             const float *__restrict__ bias, float *__restrict__ out,
-                                                            DcnDims d, long long n_pixels)
+                                                            DcnDims d, int n_base)
 {
-    const int j = threadIdx.x % G;
-    long long pixel = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool live = pixel < n_pixels;
-    if (!live) pixel = n_pixels - 1;   // keep whole warps in the shuffles; dead groups store nothing
-    const DcnPixelId p = dcn_pixel_id(pixel, d);
+    const DcnTile<G, PPG> tile(d, n_base);
+    if (!tile.row_live) return;          // whole warp
+    const int j = tile.j;
     const int K = d.kh * d.kw, C4 = d.C / 4, nblk = (C4 + G - 1) / G;
-    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)p.n * d.H * d.W * d.C);
-    float acc[COUT];
+    const long long plane = (long long)d.Ho * d.Wo;
+    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)tile.n * d.H * d.W * d.C);
+    const float *offset_n = offset + (long long)tile.n * 2 * K * plane;
+    const float *mask_n = mask ? mask + (long long)tile.n * K * plane : nullptr;
+    float acc[PPG][COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
-    DcnTapId id;
-    id.n = p.n, id.ho = p.ho, id.wo = p.wo, id.pixel = pixel;
+    for (int i = 0; i < PPG; ++i)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[i][co] = 0.f;
+    DcnPoint nxt[PPG];
+#pragma unroll
+    for (int i = 0; i < PPG; ++i) nxt[i] = dcn_load_point(offset_n, mask_n, 0, plane, tile.at[i]);
     for (int k = 0; k < K; ++k) {
-        id.k = k;
-        float h, w, m;
-        dcn_sample_point(offset, mask, id, d, h, w, m);
-        const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
-        if (!t.inside) continue;       // uniform per group; the shuffles come after the loop
-        const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
-        const float4 *r0 = img + (long long)t.row[0] * C4, *r1 = img + (long long)t.row[1] * C4;
-        const float4 *r2 = img + (long long)t.row[2] * C4, *r3 = img + (long long)t.row[3] * C4;
+        const int ky = k / d.kw, kx = k - ky * d.kw;
+        float fw[PPG][4];
+        int row[PPG][4];
+#pragma unroll
+        for (int i = 0; i < PPG; ++i) {
+            const float h = (float)(tile.ho * d.sh - d.ph + ky * d.dh) + nxt[i].oh;
+            const float w = (float)(tile.wo[i] * d.sw - d.pw + kx * d.dw) + nxt[i].ow;
+            const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);      // a sample outside the map has four zero weights
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                fw[i][q] = nxt[i].m * t.w[q];
+                row[i][q] = t.row[q] * C4;
+            }
+        }
+        if (k + 1 < K) {     // next position's offsets and mask: in flight while this one is gathered and contracted
+#pragma unroll
+            for (int i = 0; i < PPG; ++i) nxt[i] = dcn_load_point(offset_n, mask_n, k + 1, plane, tile.at[i]);
+        }
         for (int b = 0; b < nblk; ++b) {
             const int c = b * G + j;
             if (c >= C4) break;
-            const float4 a = __ldg(r0 + c), bb = __ldg(r1 + c), e = __ldg(r2 + c), f = __ldg(r3 + c);
-            float4 v;
-            v.x = f0 * a.x + f1 * bb.x + f2 * e.x + f3 * f.x;
-            v.y = f0 * a.y + f1 * bb.y + f2 * e.y + f3 * f.y;
-            v.z = f0 * a.z + f1 * bb.z + f2 * e.z + f3 * f.z;
-            v.w = f0 * a.w + f1 * bb.w + f2 * e.w + f3 * f.w;
+            float4 v[PPG];
+#pragma unroll
+            for (int i = 0; i < PPG; ++i) {
+                const float4 a = __ldg(img + row[i][0] + c), bb = __ldg(img + row[i][1] + c), e = __ldg(img + row[i][2] + c), f = __ldg(img + row[i][3] + c);
+                v[i].x = fw[i][0] * a.x + fw[i][1] * bb.x + fw[i][2] * e.x + fw[i][3] * f.x;
+                v[i].y = fw[i][0] * a.y + fw[i][1] * bb.y + fw[i][2] * e.y + fw[i][3] * f.y;
+                v[i].z = fw[i][0] * a.z + fw[i][1] * bb.z + fw[i][2] * e.z + fw[i][3] * f.z;
+                v[i].w = fw[i][0] * a.w + fw[i][1] * bb.w + fw[i][2] * e.w + fw[i][3] * f.w;
+            }
             const float4 *wk = wp + ((long long)(k * nblk + b) * COUT) * G + j;
 #pragma unroll
             for (int co = 0; co < COUT; ++co) {
                 const float4 w4 = __ldg(wk + co * G);
-                acc[co] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, acc[co]))));
+#pragma unroll
+                for (int i = 0; i < PPG; ++i)
+                    acc[i][co] = fmaf(v[i].x, w4.x, fmaf(v[i].y, w4.y, fmaf(v[i].z, w4.z, fmaf(v[i].w, w4.w, acc[i][co]))));
             }
         }
     }
-    dcn_group_sum<COUT, G>(acc, j);
-    if (!live) return;
-    float *o = out + pixel * COUT;
-    if (COUT >= G) {
-        constexpr int PER = COUT >= G ? COUT / G : 1;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) o[j * PER + i] = acc[i] + (bias ? bias[j * PER + i] : 0.f);
-    } else if (j < COUT) {
-        float mine = acc[0];
+    for (int i = 0; i < PPG; ++i) {
+        dcn_group_sum<COUT, G>(acc[i], j);
+        if (!tile.live[i]) continue;
+        float *o = out + ((long long)tile.n * plane + tile.at[i]) * COUT;
+        if (COUT >= G) {
+            constexpr int PER = COUT >= G ? COUT / G : 1;
 #pragma unroll
-        for (int i = 1; i < COUT; ++i) mine = j == i ? acc[i] : mine;
-        o[j] = mine + (bias ? bias[j] : 0.f);
+            for (int q = 0; q < PER; ++q) o[j * PER + q] = acc[i][q] + (bias ? bias[j * PER + q] : 0.f);
+        } else if (j < COUT) {
+            float mine = acc[i][0];
+#pragma unroll
+            for (int q = 1; q < COUT; ++q) mine = j == q ? acc[i][q] : mine;
+            o[j] = mine + (bias ? bias[j] : 0.f);
+        }
     }
 }
 
@@ -380,76 +429,103 @@ __global__ void __launch_bounds__(256) dcn_fused_fwd_kernel(const float *__restr
 // forms its slice of the column gradient on the fly, gc[c] = sum_co grad_out[pixel][co] * weight[co][c][k], and uses it
 // exactly like dcn_col2im_kernel uses grad_cols: corner dot products -> grad_offset / grad_mask, 16-byte vector
 // reductions -> grad_input.  The weight gradient (cols^T x grad_out) is computed by the caller from recomputed columns.
-template <int COUT, int G>
-__global__ void __launch_bounds__(256) dcn_fused_bwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+template <int COUT, int G, int PPG>
+__global__ void __launch_bounds__(256, 2) dcn_fused_bwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
                                                             const float *__restrict__ mask, const float4 *__restrict__ wp,
                                                             const float *__restrict__ grad_out /* (pixels, COUT) */,
                                                             float *__restrict__ grad_input, float *__restrict__ grad_offset,
-                                                            float *__restrict__ grad_mask, DcnDims d, long long n_pixels)
+                                                            float *__restrict__ grad_mask, DcnDims d, int n_base)
 {
-    const int j = threadIdx.x % G;
-    long long pixel = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool live = pixel < n_pixels;
-    if (!live) pixel = n_pixels - 1;
-    const DcnPixelId p = dcn_pixel_id(pixel, d);
+    const DcnTile<G, PPG> tile(d, n_base);
+    if (!tile.row_live) return;
+    const int j = tile.j;
     const int K = d.kh * d.kw, C4 = d.C / 4, nblk = (C4 + G - 1) / G;
-    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)p.n * d.H * d.W * d.C);
-    float *gimg = grad_input ? grad_input + (long long)p.n * d.H * d.W * d.C : nullptr;
-    float g[COUT];
+    const long long plane = (long long)d.Ho * d.Wo;
+    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)tile.n * d.H * d.W * d.C);
+    float *gimg = grad_input ? grad_input + (long long)tile.n * d.H * d.W * d.C : nullptr;
+    const float *offset_n = offset + (long long)tile.n * 2 * K * plane;
+    const float *mask_n = mask ? mask + (long long)tile.n * K * plane : nullptr;
+    float *goff_n = grad_offset + (long long)tile.n * 2 * K * plane;
+    float *gmask_n = grad_mask ? grad_mask + (long long)tile.n * K * plane : nullptr;
+    float g[PPG][COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) g[co] = __ldg(grad_out + pixel * COUT + co);
-    DcnTapId id;
-    id.n = p.n, id.ho = p.ho, id.wo = p.wo, id.pixel = pixel;
-    const long long plane = (long long)d.Ho * d.Wo, at = (long long)p.ho * d.Wo + p.wo;
+    for (int i = 0; i < PPG; ++i) {
+        const float *go = grad_out + ((long long)tile.n * plane + tile.at[i]) * COUT;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) g[i][co] = __ldg(go + co);
+    }
+    DcnPoint nxt[PPG];
+#pragma unroll
+    for (int i = 0; i < PPG; ++i) nxt[i] = dcn_load_point(offset_n, mask_n, 0, plane, tile.at[i]);
     for (int k = 0; k < K; ++k) {
-        id.k = k;
-        float h, w, m;
-        dcn_sample_point(offset, mask, id, d, h, w, m);
-        const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
-        float A[4] = {0.f, 0.f, 0.f, 0.f};
-        if (t.inside) {                // uniform per group
-            const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
-            for (int b = 0; b < nblk; ++b) {
-                const int c = b * G + j;
-                if (c >= C4) break;
-                const float4 *wk = wp + ((long long)(k * nblk + b) * COUT) * G + j;
-                float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ky = k / d.kw, kx = k - ky * d.kw;
+        DcnTap<float> t[PPG];
+        float fw[PPG][4], m[PPG], A[PPG][4];
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) {
-                    const float4 w4 = __ldg(wk + co * G);
-                    gc.x = fmaf(g[co], w4.x, gc.x);
-                    gc.y = fmaf(g[co], w4.y, gc.y);
-                    gc.z = fmaf(g[co], w4.z, gc.z);
-                    gc.w = fmaf(g[co], w4.w, gc.w);
+        for (int i = 0; i < PPG; ++i) {
+            const float h = (float)(tile.ho * d.sh - d.ph + ky * d.dh) + nxt[i].oh;
+            const float w = (float)(tile.wo[i] * d.sw - d.pw + kx * d.dw) + nxt[i].ow;
+            t[i] = dcn_tap(h, w, d.H, d.W);
+            m[i] = nxt[i].m;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fw[i][q] = m[i] * t[i].w[q], A[i][q] = 0.f;
+        }
+        if (k + 1 < K) {
+#pragma unroll
+            for (int i = 0; i < PPG; ++i) nxt[i] = dcn_load_point(offset_n, mask_n, k + 1, plane, tile.at[i]);
+        }
+        for (int b = 0; b < nblk; ++b) {
+            const int c = b * G + j;
+            if (c >= C4) break;
+            float4 corner[PPG][4];
+#pragma unroll
+            for (int i = 0; i < PPG; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) corner[i][q] = __ldg(img + (long long)t[i].row[q] * C4 + c);
+            const float4 *wk = wp + ((long long)(k * nblk + b) * COUT) * G + j;
+            float4 gc[PPG];
+#pragma unroll
+            for (int i = 0; i < PPG; ++i) gc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float4 w4 = __ldg(wk + co * G);
+#pragma unroll
+                for (int i = 0; i < PPG; ++i) {
+                    gc[i].x = fmaf(g[i][co], w4.x, gc[i].x);
+                    gc[i].y = fmaf(g[i][co], w4.y, gc[i].y);
+                    gc[i].z = fmaf(g[i][co], w4.z, gc[i].z);
+                    gc[i].w = fmaf(g[i][co], w4.w, gc[i].w);
                 }
-                const float4 a = __ldg(img + (long long)t.row[0] * C4 + c), bb = __ldg(img + (long long)t.row[1] * C4 + c);
-                const float4 e = __ldg(img + (long long)t.row[2] * C4 + c), f = __ldg(img + (long long)t.row[3] * C4 + c);
-                A[0] += gc.x * a.x + gc.y * a.y + gc.z * a.z + gc.w * a.w;
-                A[1] += gc.x * bb.x + gc.y * bb.y + gc.z * bb.z + gc.w * bb.w;
-                A[2] += gc.x * e.x + gc.y * e.y + gc.z * e.z + gc.w * e.w;
-                A[3] += gc.x * f.x + gc.y * f.y + gc.z * f.z + gc.w * f.w;
-                if (live && gimg) {
-                    if (f0 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[0] * C4 + c) * 4, f0 * gc.x, f0 * gc.y, f0 * gc.z, f0 * gc.w);
-                    if (f1 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[1] * C4 + c) * 4, f1 * gc.x, f1 * gc.y, f1 * gc.z, f1 * gc.w);
-                    if (f2 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[2] * C4 + c) * 4, f2 * gc.x, f2 * gc.y, f2 * gc.z, f2 * gc.w);
-                    if (f3 != 0.f) dcn_red_add_f4(gimg + ((long long)t.row[3] * C4 + c) * 4, f3 * gc.x, f3 * gc.y, f3 * gc.z, f3 * gc.w);
+            }
+#pragma unroll
+            for (int i = 0; i < PPG; ++i) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 r = corner[i][q];
+                    A[i][q] += gc[i].x * r.x + gc[i].y * r.y + gc[i].z * r.z + gc[i].w * r.w;
+                    const float f = fw[i][q];
+                    if (gimg && tile.live[i] && f != 0.f)
+                        dcn_red_add_f4(gimg + ((long long)t[i].row[q] * C4 + c) * 4, f * gc[i].x, f * gc[i].y, f * gc[i].z, f * gc[i].w);
                 }
             }
         }
 #pragma unroll
-        for (int o = G / 2; o >= 1; o >>= 1) {
+        for (int i = 0; i < PPG; ++i) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) A[i] += __shfl_xor_sync(0xffffffffu, A[i], o, G);
-        }
-        if (live && j == 0) {
-            const float A0 = t.ok[0] ? A[0] : 0.f, A1 = t.ok[1] ? A[1] : 0.f;
-            const float A2 = t.ok[2] ? A[2] : 0.f, A3 = t.ok[3] ? A[3] : 0.f;
-            const float val = t.hh * (t.hw * A0 + t.lw * A1) + t.lh * (t.hw * A2 + t.lw * A3);
-            const float gh = t.hw * (A2 - A0) + t.lw * (A3 - A1);
-            const float gw = t.hh * (A1 - A0) + t.lh * (A3 - A2);
-            grad_offset[((long long)p.n * 2 * K + 2 * k) * plane + at] = t.inside ? m * gh : 0.f;
-            grad_offset[((long long)p.n * 2 * K + 2 * k + 1) * plane + at] = t.inside ? m * gw : 0.f;
-            if (grad_mask) grad_mask[((long long)p.n * K + k) * plane + at] = t.inside ? val : 0.f;
+            for (int o = G / 2; o >= 1; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) A[i][q] += __shfl_xor_sync(0xffffffffu, A[i][q], o, G);
+            if (tile.live[i] && j == 0) {
+                // outside corners carry garbage from their clamped rows: zero them like the zero padding does
+                const float A0 = t[i].ok[0] ? A[i][0] : 0.f, A1 = t[i].ok[1] ? A[i][1] : 0.f;
+                const float A2 = t[i].ok[2] ? A[i][2] : 0.f, A3 = t[i].ok[3] ? A[i][3] : 0.f;
+                const float val = t[i].hh * (t[i].hw * A0 + t[i].lw * A1) + t[i].lh * (t[i].hw * A2 + t[i].lw * A3);
+                const float gh = t[i].hw * (A2 - A0) + t[i].lw * (A3 - A1);
+                const float gw = t[i].hh * (A1 - A0) + t[i].lh * (A3 - A2);
+                goff_n[(2 * k) * plane + tile.at[i]] = t[i].inside ? m[i] * gh : 0.f;
+                goff_n[(2 * k + 1) * plane + tile.at[i]] = t[i].inside ? m[i] * gw : 0.f;
+                if (gmask_n) gmask_n[k * plane + tile.at[i]] = t[i].inside ? val : 0.f;
+            }
         }
     }
 }

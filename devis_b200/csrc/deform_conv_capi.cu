@@ -17,25 +17,34 @@ int check_dims(const DcnDims &d, int dtype)
     return DEVIS_MSDA_OK;
 }
 
-// lanes per tap: a group covers its channels in 16-byte pieces; 8 lanes = one 128-byte line per corner row
+// lanes per tap: a group covers its channels in 16-byte pieces; 8 lanes = one 128-byte line per corner row.
+// Grid: x = output plane (wo fastest), y = kernel position, z = batch item (in slices of at most 65535).
+constexpr int kMaxGridZ = 65535;
+
 template <class F4, class F8, class S8, class S32>
-int dispatch(const DcnDims &d, int dtype, long long n_taps, F4 f4, F8 f8, S8 s8, S32 s32)
+int dispatch(const DcnDims &d, int dtype, F4 f4, F8 f8, S8 s8, S32 s32)
 {
-    if (n_taps == 0) return DEVIS_MSDA_OK;
+    const long long plane = (long long)d.Ho * d.Wo;
+    if (d.N == 0 || plane == 0) return DEVIS_MSDA_OK;
     int G;
     const bool vec = dtype == DEVIS_MSDA_F32 && d.C % 4 == 0;
     if (vec) G = d.C / 4 >= 8 ? 8 : 4;
     else G = d.C >= 32 ? 32 : 8;
-    const long long blocks = (n_taps * G + 255) / 256;
-    if (blocks > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
-    if (vec) {
-        if (G == 8) f8((unsigned)blocks);
-        else f4((unsigned)blocks);
-    } else {
-        if (G == 32) s32((unsigned)blocks);
-        else s8((unsigned)blocks);
+    if (plane * G + 255 >= (1LL << 31) || d.kh * d.kw > 65535) return DEVIS_MSDA_ERR_TOO_LARGE;
+    for (int n0 = 0; n0 < d.N; n0 += kMaxGridZ) {
+        const dim3 grid((unsigned)((plane * G + 255) / 256), (unsigned)(d.kh * d.kw),
+                        (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));
+        if (vec) {
+            if (G == 8) f8(grid, n0);
+            else f4(grid, n0);
+        } else {
+            if (G == 32) s32(grid, n0);
+            else s8(grid, n0);
+        }
+        const int rc = devis_capi_check_launch();
+        if (rc) return rc;
     }
-    return devis_capi_check_launch();
+    return DEVIS_MSDA_OK;
 }
 
 }  // namespace
@@ -56,17 +65,17 @@ int devis_dcn_im2col(const void *input, const void *offset, const void *mask, vo
     if (dtype == DEVIS_MSDA_F32) {
         const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
         float *co = (float *)cols;
-        return dispatch(d, dtype, n_taps,
-                        [&](unsigned b) { dcn_im2col_kernel<float, 4, 4><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
-                        [&](unsigned b) { dcn_im2col_kernel<float, 4, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
-                        [&](unsigned b) { dcn_im2col_kernel<float, 1, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
-                        [&](unsigned b) { dcn_im2col_kernel<float, 1, 32><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); });
+        return dispatch(d, dtype,
+                        [&](dim3 b, int n0) { dcn_im2col_kernel<float, 4, 4><<<b, 256, 0, st>>>(in, of, mk, co, d, n0); },
+                        [&](dim3 b, int n0) { dcn_im2col_kernel<float, 4, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n0); },
+                        [&](dim3 b, int n0) { dcn_im2col_kernel<float, 1, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n0); },
+                        [&](dim3 b, int n0) { dcn_im2col_kernel<float, 1, 32><<<b, 256, 0, st>>>(in, of, mk, co, d, n0); });
     }
     const double *in = (const double *)input, *of = (const double *)offset, *mk = (const double *)mask;
     double *co = (double *)cols;
-    return dispatch(d, dtype, n_taps, [&](unsigned) {}, [&](unsigned) {},
-                    [&](unsigned b) { dcn_im2col_kernel<double, 1, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); },
-                    [&](unsigned b) { dcn_im2col_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, co, d, n_taps); });
+    return dispatch(d, dtype, [&](dim3, int) {}, [&](dim3, int) {},
+                    [&](dim3 b, int n0) { dcn_im2col_kernel<double, 1, 8><<<b, 256, 0, st>>>(in, of, mk, co, d, n0); },
+                    [&](dim3 b, int n0) { dcn_im2col_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, co, d, n0); });
 }
 
 int devis_dcn_col2im(const void *input, const void *offset, const void *mask, const void *grad_cols, void *grad_input,
@@ -93,18 +102,18 @@ int devis_dcn_col2im(const void *input, const void *offset, const void *mask, co
         const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
         const float *gc = (const float *)grad_cols;
         float *gi = (float *)grad_input, *go = (float *)grad_offset, *gm = (float *)grad_mask;
-        return dispatch(d, dtype, n_taps,
-                        [&](unsigned b) { dcn_col2im_kernel<float, 4, 4><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
-                        [&](unsigned b) { dcn_col2im_kernel<float, 4, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
-                        [&](unsigned b) { dcn_col2im_kernel<float, 1, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
-                        [&](unsigned b) { dcn_col2im_kernel<float, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); });
+        return dispatch(d, dtype,
+                        [&](dim3 b, int n0) { dcn_col2im_kernel<float, 4, 4><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n0); },
+                        [&](dim3 b, int n0) { dcn_col2im_kernel<float, 4, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n0); },
+                        [&](dim3 b, int n0) { dcn_col2im_kernel<float, 1, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n0); },
+                        [&](dim3 b, int n0) { dcn_col2im_kernel<float, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n0); });
     }
     const double *in = (const double *)input, *of = (const double *)offset, *mk = (const double *)mask;
     const double *gc = (const double *)grad_cols;
     double *gi = (double *)grad_input, *go = (double *)grad_offset, *gm = (double *)grad_mask;
-    return dispatch(d, dtype, n_taps, [&](unsigned) {}, [&](unsigned) {},
-                    [&](unsigned b) { dcn_col2im_kernel<double, 1, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); },
-                    [&](unsigned b) { dcn_col2im_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n_taps); });
+    return dispatch(d, dtype, [&](dim3, int) {}, [&](dim3, int) {},
+                    [&](dim3 b, int n0) { dcn_col2im_kernel<double, 1, 8><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n0); },
+                    [&](dim3 b, int n0) { dcn_col2im_kernel<double, 1, 32><<<b, 256, 0, st>>>(in, of, mk, gc, gi, go, gm, d, n0); });
 }
 
 
@@ -145,15 +154,24 @@ int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int ou
     return devis_capi_check_launch();
 }
 
-#define DCN_FUSED_CASES(KERNEL, G, ...)                                                      \
-    switch (out_channels) {                                                                  \
-    case 1: KERNEL<1, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
-    case 2: KERNEL<2, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
-    case 4: KERNEL<4, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
-    case 8: KERNEL<8, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                        \
-    case 16: KERNEL<16, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                      \
-    case 32: KERNEL<32, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                      \
-    default: KERNEL<64, G><<<blocks, 256, 0, st>>>(__VA_ARGS__); break;                      \
+// pixels per lane group: the weights fetched for one (position, channel block) serve PPG pixels
+#define DCN_FUSED_LAUNCH(KERNEL, COUT, G, PPG, ...)                                                          \
+    for (int n0 = 0; n0 < d.N; n0 += kMaxGridZ) {                                                            \
+        const dim3 grid((unsigned)((d.Wo + (32 / G) * PPG - 1) / ((32 / G) * PPG)), (unsigned)((d.Ho + 7) / 8), \
+                        (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));                            \
+        KERNEL<COUT, G, PPG><<<grid, 256, 0, st>>>(__VA_ARGS__, d, n0);                                      \
+        const int rc_ = devis_capi_check_launch();                                                           \
+        if (rc_) return rc_;                                                                                 \
+    }
+#define DCN_FUSED_CASES(KERNEL, G, PPG, PPG32, ...)                              \
+    switch (out_channels) {                                                      \
+    case 1: DCN_FUSED_LAUNCH(KERNEL, 1, G, PPG, __VA_ARGS__) break;              \
+    case 2: DCN_FUSED_LAUNCH(KERNEL, 2, G, PPG, __VA_ARGS__) break;              \
+    case 4: DCN_FUSED_LAUNCH(KERNEL, 4, G, PPG, __VA_ARGS__) break;              \
+    case 8: DCN_FUSED_LAUNCH(KERNEL, 8, G, PPG, __VA_ARGS__) break;              \
+    case 16: DCN_FUSED_LAUNCH(KERNEL, 16, G, PPG, __VA_ARGS__) break;            \
+    case 32: DCN_FUSED_LAUNCH(KERNEL, 32, G, PPG32, __VA_ARGS__) break;          \
+    default: DCN_FUSED_LAUNCH(KERNEL, 64, G, 1, __VA_ARGS__) break;              \
     }
 
 int devis_dcn_fused_forward(const void *input, const void *offset, const void *mask, const void *packed_weight,
@@ -170,17 +188,16 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
     const long long n_pixels = (long long)batch * out_h * out_w;
     if (n_pixels == 0) return DEVIS_MSDA_OK;
     if (!input || !offset || !packed_weight || !out) return DEVIS_MSDA_ERR_NULL_POINTER;
-    const long long nb = (n_pixels * G + 255) / 256;
-    if (nb > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
-    const unsigned blocks = (unsigned)nb;
+    if ((long long)out_h * out_w >= (1LL << 31) || (long long)height * width * channels >= (1LL << 31))
+        return DEVIS_MSDA_ERR_TOO_LARGE;
     cudaStream_t st = (cudaStream_t)stream;
     const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
     const float4 *wp = (const float4 *)packed_weight;
     const float *bs = (const float *)bias;
     float *o = (float *)out;
-    if (G == 8) { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 8, in, of, mk, wp, bs, o, d, n_pixels) }
-    else { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 4, in, of, mk, wp, bs, o, d, n_pixels) }
-    return devis_capi_check_launch();
+    if (G == 8) { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 8, 2, 2, in, of, mk, wp, bs, o) }
+    else { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 4, 2, 2, in, of, mk, wp, bs, o) }
+    return DEVIS_MSDA_OK;
 }
 
 int devis_dcn_fused_backward(const void *input, const void *offset, const void *mask, const void *packed_weight,
@@ -207,16 +224,15 @@ int devis_dcn_fused_backward(const void *input, const void *offset, const void *
         }
     }
     if (n_pixels == 0) return DEVIS_MSDA_OK;
-    const long long nb = (n_pixels * G + 255) / 256;
-    if (nb > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
-    const unsigned blocks = (unsigned)nb;
+    if ((long long)out_h * out_w >= (1LL << 31) || (long long)height * width * channels >= (1LL << 31))
+        return DEVIS_MSDA_ERR_TOO_LARGE;
     const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
     const float4 *wp = (const float4 *)packed_weight;
     const float *go = (const float *)grad_out;
     float *gi = (float *)grad_input, *gof = (float *)grad_offset, *gm = (float *)grad_mask;
-    if (G == 8) { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 8, in, of, mk, wp, go, gi, gof, gm, d, n_pixels) }
-    else { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 4, in, of, mk, wp, go, gi, gof, gm, d, n_pixels) }
-    return devis_capi_check_launch();
+    if (G == 8) { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 8, 1, 1, in, of, mk, wp, go, gi, gof, gm) }
+    else { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 4, 1, 1, in, of, mk, wp, go, gi, gof, gm) }
+    return DEVIS_MSDA_OK;
 }
 
 }  // extern "C"
