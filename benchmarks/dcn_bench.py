@@ -110,19 +110,22 @@ def main():
             x.data_ptr(), off.data_ptr(), m.data_ptr(), gcols.data_ptr(), gx.data_ptr(), goff.data_ptr(), gm.data_ptr(),
             *dims, _lib.F32, st)), args.iters)
         # fused gather + contraction kernels (layers they serve), same way
-        if lib.devis_dcn_fused_lanes(cin, cout, _lib.F32):
+        form = lib.devis_dcn_fused_form(cin, cout, 3, 3, _lib.F32)
+        if form:
             packed = torch.empty(int(lib.devis_dcn_packed_weight_elems(cin, cout, 3, 3)), device="cuda")
             _lib.check(lib.devis_dcn_pack_weight(wt.data_ptr(), packed.data_ptr(), cin, cout, 3, 3, st))
             out = torch.empty(n, h, w, cout, device="cuda")
             gl = gout.permute(0, 2, 3, 1).contiguous()
+        if form & 1:
             row["fused_fwd_kernel_us"] = _time(lambda: _lib.check(lib.devis_dcn_fused_forward(
                 x.data_ptr(), off.data_ptr(), m.data_ptr(), packed.data_ptr(), b.data_ptr(), out.data_ptr(), *dims, cout,
                 st)), args.iters)
+            fb = 4 * (x.numel() + off.numel() + m.numel() + out.numel())
+            row["fused_fwd_GBps"] = fb / row["fused_fwd_kernel_us"] / 1e3
+        if form & 2:
             row["fused_bwd_kernel_us"] = _time(lambda: _lib.check(lib.devis_dcn_fused_backward(
                 x.data_ptr(), off.data_ptr(), m.data_ptr(), packed.data_ptr(), gl.data_ptr(), gx.data_ptr(),
                 goff.data_ptr(), gm.data_ptr(), *dims, cout, st)), args.iters)
-            fb = 4 * (x.numel() + off.numel() + m.numel() + out.numel())
-            row["fused_fwd_GBps"] = fb / row["fused_fwd_kernel_us"] / 1e3
             bb = 4 * (x.numel() + off.numel() + m.numel() + gl.numel() + gx.numel() + goff.numel() + gm.numel())
             row["fused_bwd_GBps"] = bb / row["fused_bwd_kernel_us"] / 1e3
         # algorithmic bytes of the gather: input + offset + mask read once, columns written once

@@ -36,7 +36,7 @@ SIGNATURES = {
     # include/devis_deform_conv.h
     "devis_dcn_im2col": (_i, [_vp] * 4 + [_i] * 15 + [_vp]),
     "devis_dcn_col2im": (_i, [_vp] * 7 + [_i] * 15 + [_vp]),
-    "devis_dcn_fused_lanes": (_i, [_i] * 3),
+    "devis_dcn_fused_form": (_i, [_i] * 5),
     "devis_dcn_packed_weight_elems": (_sz, [_i] * 4),
     "devis_dcn_pack_weight": (_i, [_vp] * 2 + [_i] * 4 + [_vp]),
     "devis_dcn_fused_forward": (_i, [_vp] * 6 + [_i] * 15 + [_vp]),

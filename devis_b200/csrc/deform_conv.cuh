@@ -530,4 +530,129 @@ __global__ void __launch_bounds__(256, 2) dcn_fused_bwd_kernel(const float *__re
     }
 }
 
+// =====================================================================================================================
+// Fused forward with the weights in CONSTANT memory (layers with 16, 32, 48 or 64 output channels and kh*kw*C <= 1024).
+//
+// The lane-group kernel above fetches a float4 of weights per lane for every 4 (x PPG) multiply-adds: the register-file
+// delivery of those loads (4 data-pipe wavefronts per LDG.128, broadcast or not) costs more than the arithmetic they
+// feed.  Here the contraction is turned around: a THREAD owns one output pixel and 16 output channels, so the weight of
+// (k, c, co) is the same for every lane of the warp and comes straight out of the constant bank as an operand of the
+// FFMA -- no load instruction, no data-pipe traffic.  A block owns a tile of 8 x 32 output pixels and alternates, per
+// kernel position k:
+//   gather      groups of 8 lanes interpolate the C channels of one (pixel, k) each -- coalesced 16-byte gathers exactly
+//               like dcn_im2col_kernel -- and park them in shared memory as cols_s[c][pixel] (row stride 257: the 32
+//               lanes of a warp hit 32 different banks on the way in, consecutive pixels on the way out);
+//   contract    thread p: acc[co] += cols_s[c][p] * W[k][c][co] for all c, 16 FFMAs per shared-memory word.
+// Several blocks per SM overlap one block's gathers with another's arithmetic.  Output channels beyond 16 are served by
+// further launches (one 16-channel tile of the weights in the constant bank at a time).
+// =====================================================================================================================
+constexpr int kDcnConstFloats = 16384;                 // 64 KB
+__constant__ __align__(16) float dcn_cw[kDcnConstFloats];            // [k][c][16] of the current 16-channel tile
+constexpr int kDcnCTileW = 32, kDcnCTileH = 8, kDcnCStride = kDcnCTileW * kDcnCTileH + 1;
+
+// packed layout for this form: wc[((t * K + k) * C + c) * 16 + q] = weight[16 t + q][c][k]
+__global__ void dcn_pack_weight_const_kernel(const float *__restrict__ w /* (Cout, C, K) */, float *__restrict__ wc, int cout,
+                                             int C, int K)
+{
+    const int total = cout * C * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int q = i & 15;
+        int r = i >> 4;
+        const int c = r % C;
+        r /= C;
+        const int k = r % K, t = r / K;
+        wc[i] = w[((long long)(16 * t + q) * C + c) * K + k];
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, 3) dcn_fusedc_fwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+                                                                const float *__restrict__ mask, const float *__restrict__ bias,
+                                                                float *__restrict__ out, DcnDims d, int n_base, int cout,
+                                                                int co0)
+{
+    extern __shared__ float cols_s[];                  // [C][kDcnCStride]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 7, grp = lane >> 3;
+    const int n = n_base + (int)blockIdx.z;
+    const int ty0 = (int)blockIdx.y * kDcnCTileH, tx0 = (int)blockIdx.x * kDcnCTileW;
+    constexpr int C4 = C / 4, nblk = (C4 + 7) / 8;
+    const int K = d.kh * d.kw;
+    const long long plane = (long long)d.Ho * d.Wo;
+    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)n * d.H * d.W * C);
+    const float *offset_n = offset + (long long)n * 2 * K * plane;
+    const float *mask_n = mask ? mask + (long long)n * K * plane : nullptr;
+
+    // gather role: this group serves tile pixels p = it * 32 + warp * 4 + grp, it = 0..7 (row it, column warp*4+grp);
+    // lane j of the group fetches the sampling point of the group's j-th pixel and hands it over by shuffle
+    const int gx = tx0 + warp * 4 + grp;
+    const int my_y = ty0 + j;                            // pixel whose offsets this lane fetches
+    const bool my_live = my_y < d.Ho && gx < d.Wo;
+    const long long my_at = (long long)min(my_y, d.Ho - 1) * d.Wo + min(gx, d.Wo - 1);
+    // contract role: thread owns tile pixel threadIdx.x = row (threadIdx.x / 32), column lane
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+
+    DcnPoint nxt = dcn_load_point(offset_n, mask_n, 0, plane, my_at);
+    int wbase = 0;     // its own induction variable: untouched by the divergent gather code, it stays in a uniform register
+    for (int k = 0; k < K; ++k, wbase += C * 4) {
+        const int ky = k / d.kw, kx = k - ky * d.kw;
+        const DcnPoint cur = nxt;
+        if (k + 1 < K) nxt = dcn_load_point(offset_n, mask_n, k + 1, plane, my_at);
+        if (k > 0) __syncthreads();                      // everyone is done reading the previous position's columns
+#pragma unroll 2
+        for (int it = 0; it < kDcnCTileH; ++it) {
+            const float oh = __shfl_sync(0xffffffffu, cur.oh, it, 8), ow = __shfl_sync(0xffffffffu, cur.ow, it, 8);
+            const float m = __shfl_sync(0xffffffffu, cur.m, it, 8);
+            const bool live = __shfl_sync(0xffffffffu, (int)my_live, it, 8) != 0;
+            if (!live) continue;                         // uniform per group; dead pixels' columns are never read
+            const float h = (float)((ty0 + it) * d.sh - d.ph + ky * d.dh) + oh;
+            const float w = (float)(gx * d.sw - d.pw + kx * d.dw) + ow;
+            const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
+            const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
+            const float4 *r0 = img + t.row[0] * C4, *r1 = img + t.row[1] * C4, *r2 = img + t.row[2] * C4, *r3 = img + t.row[3] * C4;
+            float *dst = cols_s + it * 32 + warp * 4 + grp;
+#pragma unroll
+            for (int b = 0; b < nblk; ++b) {
+                const int c = b * 8 + j;
+                if (c >= C4) break;
+                const float4 a = __ldg(r0 + c), bb = __ldg(r1 + c), e = __ldg(r2 + c), f = __ldg(r3 + c);
+                dst[(4 * c + 0) * kDcnCStride] = f0 * a.x + f1 * bb.x + f2 * e.x + f3 * f.x;
+                dst[(4 * c + 1) * kDcnCStride] = f0 * a.y + f1 * bb.y + f2 * e.y + f3 * f.y;
+                dst[(4 * c + 2) * kDcnCStride] = f0 * a.z + f1 * bb.z + f2 * e.z + f3 * f.z;
+                dst[(4 * c + 3) * kDcnCStride] = f0 * a.w + f1 * bb.w + f2 * e.w + f3 * f.w;
+            }
+        }
+        __syncthreads();
+        // C is a compile-time constant and the loop is unrolled: the weight addresses are (uniform base + immediate), the
+        // compiler fetches them with uniform constant loads (LDCU into uniform registers) and feeds the FFMAs from
+        // there -- no per-thread load, nothing on the L1 data pipe
+        const float *col = cols_s + threadIdx.x;
+        const float4 *wk = reinterpret_cast<const float4 *>(dcn_cw) + wbase;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float v = col[c * kDcnCStride];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = wk[c * 4 + q];
+                acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+            }
+        }
+    }
+    const int oy = ty0 + warp, ox = tx0 + lane;
+    if (oy >= d.Ho || ox >= d.Wo) return;
+    float4 *o = reinterpret_cast<float4 *>(out + ((long long)n * plane + (long long)oy * d.Wo + ox) * cout + co0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 v = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        if (bias) {
+            v.x += bias[co0 + 4 * q], v.y += bias[co0 + 4 * q + 1], v.z += bias[co0 + 4 * q + 2], v.w += bias[co0 + 4 * q + 3];
+        }
+        o[q] = v;
+    }
+}
+
 }  // namespace devis

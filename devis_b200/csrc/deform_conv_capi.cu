@@ -3,6 +3,8 @@
 #include "capi_common.h"
 #include "deform_conv.cuh"
 
+#include <mutex>
+
 using namespace devis;
 
 namespace {
@@ -117,41 +119,96 @@ int devis_dcn_col2im(const void *input, const void *offset, const void *mask, co
 }
 
 
+}  // extern "C"
+
 // ---- fused gather + contraction (no column matrix) -------------------------------------------------------------------
 
-static int fused_lanes(int channels, int out_channels, int dtype)
+namespace {
+
+// which fused kernels serve a layer, and what the packed weight buffer holds for it
+struct FusedPlan {
+    int G = 0;                 // lanes per pixel of the lane-group kernels
+    bool lanes_fwd = false;    // forward by dcn_fused_fwd_kernel
+    bool lanes_bwd = false;    // data backward by dcn_fused_bwd_kernel
+    bool constant = false;     // forward by dcn_fusedc_fwd_kernel (weights in the constant bank)
+    size_t lanes_elems = 0, const_elems = 0;   // packed buffer = [lane-group layout | constant layout]
+    bool any() const { return lanes_fwd || lanes_bwd || constant; }
+};
+
+FusedPlan fused_plan(int C, int cout, int kh, int kw, int dtype)
 {
-    if (dtype != DEVIS_MSDA_F32 || channels <= 0 || channels % 4) return 0;
-    switch (out_channels) {
-    case 1: case 2: case 4: case 8: case 16: case 32: case 64: break;
-    default: return 0;
-    }
-    return channels / 4 > 4 ? 8 : 4;
+    FusedPlan p;
+    if (dtype != DEVIS_MSDA_F32 || C <= 0 || C % 4 || kh <= 0 || kw <= 0 || cout <= 0) return p;
+    const long long K = (long long)kh * kw;
+    const bool small = cout == 1 || cout == 2 || cout == 4 || cout == 8 || cout == 16;
+    p.G = C / 4 > 4 ? 8 : 4;
+    const bool c_served = C == 16 || C == 32 || C == 40 || C == 64 || C == 72;   // dcn_fusedc_fwd_kernel<C> instantiations
+    p.constant = c_served && cout % 16 == 0 && cout <= 64 && K * C * 16 <= kDcnConstFloats;
+    p.lanes_bwd = small;
+    p.lanes_fwd = small && !p.constant;
+    if (p.lanes_fwd || p.lanes_bwd) p.lanes_elems = (size_t)K * ((C / 4 + p.G - 1) / p.G) * cout * p.G * 4;
+    if (p.constant) p.const_elems = (size_t)K * C * cout;
+    return p;
 }
 
-int devis_dcn_fused_lanes(int channels, int out_channels, int dtype) { return fused_lanes(channels, out_channels, dtype); }
+// the one constant bank is shared by every stream of the process: calls are serialised by a mutex on the host and by an
+// event on the device (a call on another stream waits for the previous call's kernels before it overwrites the bank)
+std::mutex g_const_mutex;
+cudaEvent_t g_const_event = nullptr;
+cudaStream_t g_const_stream = nullptr;
+bool g_const_used = false, g_const_attr = false;
+
+bool stream_is_capturing(cudaStream_t st)
+{
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return status != cudaStreamCaptureStatusNone;
+}
+
+}  // namespace
+
+extern "C" {
+
+int devis_dcn_fused_form(int channels, int out_channels, int kernel_h, int kernel_w, int dtype)
+{
+    const FusedPlan p = fused_plan(channels, out_channels, kernel_h, kernel_w, dtype);
+    return ((p.lanes_fwd || p.constant) ? 1 : 0) | (p.lanes_bwd ? 2 : 0);
+}
 
 size_t devis_dcn_packed_weight_elems(int channels, int out_channels, int kernel_h, int kernel_w)
 {
-    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
-    if (!G || kernel_h <= 0 || kernel_w <= 0) return 0;
-    const int nblk = (channels / 4 + G - 1) / G;
-    return (size_t)kernel_h * kernel_w * nblk * out_channels * G * 4;
+    const FusedPlan p = fused_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    return p.lanes_elems + p.const_elems;
 }
 
 int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int out_channels, int kernel_h, int kernel_w,
                           void *stream)
 {
-    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
-    if (!G) return DEVIS_MSDA_ERR_UNSUPPORTED;
-    if (kernel_h <= 0 || kernel_w <= 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (kernel_h <= 0 || kernel_w <= 0 || channels <= 0 || out_channels <= 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    const FusedPlan p = fused_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    if (!p.any()) return DEVIS_MSDA_ERR_UNSUPPORTED;
     if (!weight || !packed) return DEVIS_MSDA_ERR_NULL_POINTER;
-    const int nblk = (channels / 4 + G - 1) / G, K = kernel_h * kernel_w;
-    const long long total = (long long)K * nblk * out_channels * G * 4;
-    const unsigned blocks = (unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
-    dcn_pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float *)weight, (float *)packed, out_channels,
-                                                                    channels, K, G, nblk);
-    return devis_capi_check_launch();
+    const int K = kernel_h * kernel_w;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.lanes_elems) {
+        const int nblk = (channels / 4 + p.G - 1) / p.G;
+        const unsigned blocks = (unsigned)((p.lanes_elems + 255) / 256 > 1184 ? 1184 : (p.lanes_elems + 255) / 256);
+        dcn_pack_weight_kernel<<<blocks, 256, 0, st>>>((const float *)weight, (float *)packed, out_channels, channels, K,
+                                                       p.G, nblk);
+        const int rc = devis_capi_check_launch();
+        if (rc) return rc;
+    }
+    if (p.const_elems) {
+        const unsigned blocks = (unsigned)((p.const_elems + 255) / 256 > 1184 ? 1184 : (p.const_elems + 255) / 256);
+        dcn_pack_weight_const_kernel<<<blocks, 256, 0, st>>>((const float *)weight, (float *)packed + p.lanes_elems,
+                                                             out_channels, channels, K);
+        const int rc = devis_capi_check_launch();
+        if (rc) return rc;
+    }
+    return DEVIS_MSDA_OK;
 }
 
 // pixels per lane group: the weights fetched for one (position, channel block) serve PPG pixels
@@ -163,15 +220,13 @@ int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int ou
         const int rc_ = devis_capi_check_launch();                                                           \
         if (rc_) return rc_;                                                                                 \
     }
-#define DCN_FUSED_CASES(KERNEL, G, PPG, PPG32, ...)                              \
+#define DCN_FUSED_CASES(KERNEL, G, PPG, ...)                                     \
     switch (out_channels) {                                                      \
     case 1: DCN_FUSED_LAUNCH(KERNEL, 1, G, PPG, __VA_ARGS__) break;              \
     case 2: DCN_FUSED_LAUNCH(KERNEL, 2, G, PPG, __VA_ARGS__) break;              \
     case 4: DCN_FUSED_LAUNCH(KERNEL, 4, G, PPG, __VA_ARGS__) break;              \
     case 8: DCN_FUSED_LAUNCH(KERNEL, 8, G, PPG, __VA_ARGS__) break;              \
-    case 16: DCN_FUSED_LAUNCH(KERNEL, 16, G, PPG, __VA_ARGS__) break;            \
-    case 32: DCN_FUSED_LAUNCH(KERNEL, 32, G, PPG32, __VA_ARGS__) break;          \
-    default: DCN_FUSED_LAUNCH(KERNEL, 64, G, 1, __VA_ARGS__) break;              \
+    default: DCN_FUSED_LAUNCH(KERNEL, 16, G, PPG, __VA_ARGS__) break;            \
     }
 
 int devis_dcn_fused_forward(const void *input, const void *offset, const void *mask, const void *packed_weight,
@@ -183,8 +238,8 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
                     stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
     const int rc = check_dims(d, DEVIS_MSDA_F32);
     if (rc) return rc;
-    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
-    if (!G) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const FusedPlan plan = fused_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    if (!plan.lanes_fwd && !plan.constant) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const long long n_pixels = (long long)batch * out_h * out_w;
     if (n_pixels == 0) return DEVIS_MSDA_OK;
     if (!input || !offset || !packed_weight || !out) return DEVIS_MSDA_ERR_NULL_POINTER;
@@ -192,11 +247,58 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
         return DEVIS_MSDA_ERR_TOO_LARGE;
     cudaStream_t st = (cudaStream_t)stream;
     const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask;
-    const float4 *wp = (const float4 *)packed_weight;
     const float *bs = (const float *)bias;
     float *o = (float *)out;
-    if (G == 8) { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 8, 2, 2, in, of, mk, wp, bs, o) }
-    else { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 4, 2, 2, in, of, mk, wp, bs, o) }
+    if (plan.constant) {
+        const float *wc = (const float *)packed_weight + plan.lanes_elems;
+        const size_t tile_floats = (size_t)kernel_h * kernel_w * channels * 16;
+        const size_t smem = (size_t)channels * kDcnCStride * sizeof(float);
+        std::lock_guard<std::mutex> lock(g_const_mutex);
+        void (*kernel)(const float *, const float *, const float *, const float *, float *, DcnDims, int, int, int) =
+            channels == 16 ? dcn_fusedc_fwd_kernel<16> : channels == 32 ? dcn_fusedc_fwd_kernel<32> :
+            channels == 40 ? dcn_fusedc_fwd_kernel<40> : channels == 64 ? dcn_fusedc_fwd_kernel<64> : dcn_fusedc_fwd_kernel<72>;
+        if (!g_const_attr) {
+            cudaError_t e = cudaSuccess;
+            const int most = 72 * kDcnCStride * (int)sizeof(float);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(dcn_fusedc_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(dcn_fusedc_fwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+            g_const_attr = true;
+        }
+        const bool capturing = stream_is_capturing(st);
+        if (!capturing) {
+            if (!g_const_event) {
+                const cudaError_t e = cudaEventCreateWithFlags(&g_const_event, cudaEventDisableTiming);
+                if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+            }
+            if (g_const_used && g_const_stream != st) {
+                const cudaError_t e = cudaStreamWaitEvent(st, g_const_event, 0);
+                if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+            }
+        }
+        for (int t = 0; t < out_channels / 16; ++t) {
+            const cudaError_t e = cudaMemcpyToSymbolAsync(dcn_cw, wc + t * tile_floats, tile_floats * sizeof(float), 0,
+                                                          cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+            for (int n0 = 0; n0 < d.N; n0 += kMaxGridZ) {
+                const dim3 grid((unsigned)((d.Wo + kDcnCTileW - 1) / kDcnCTileW), (unsigned)((d.Ho + kDcnCTileH - 1) / kDcnCTileH),
+                                (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));
+                kernel<<<grid, 256, smem, st>>>(in, of, mk, bs, o, d, n0, out_channels, 16 * t);
+                const int rc_ = devis_capi_check_launch();
+                if (rc_) return rc_;
+            }
+        }
+        if (!capturing) {
+            const cudaError_t e = cudaEventRecord(g_const_event, st);
+            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+            g_const_used = true;
+            g_const_stream = st;
+        }
+        return DEVIS_MSDA_OK;
+    }
+    const float4 *wp = (const float4 *)packed_weight;
+    if (plan.G == 8) { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 8, 2, in, of, mk, wp, bs, o) }
+    else { DCN_FUSED_CASES(dcn_fused_fwd_kernel, 4, 2, in, of, mk, wp, bs, o) }
     return DEVIS_MSDA_OK;
 }
 
@@ -210,8 +312,8 @@ int devis_dcn_fused_backward(const void *input, const void *offset, const void *
                     stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
     const int rc = check_dims(d, DEVIS_MSDA_F32);
     if (rc) return rc;
-    const int G = fused_lanes(channels, out_channels, DEVIS_MSDA_F32);
-    if (!G) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const FusedPlan plan = fused_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    if (!plan.lanes_bwd) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const long long n_pixels = (long long)batch * out_h * out_w;
     if (n_pixels > 0 && (!input || !offset || !packed_weight || !grad_out || !grad_offset || (mask && !grad_mask)))
         return DEVIS_MSDA_ERR_NULL_POINTER;
@@ -230,8 +332,8 @@ int devis_dcn_fused_backward(const void *input, const void *offset, const void *
     const float4 *wp = (const float4 *)packed_weight;
     const float *go = (const float *)grad_out;
     float *gi = (float *)grad_input, *gof = (float *)grad_offset, *gm = (float *)grad_mask;
-    if (G == 8) { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 8, 1, 1, in, of, mk, wp, go, gi, gof, gm) }
-    else { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 4, 1, 1, in, of, mk, wp, go, gi, gof, gm) }
+    if (plan.G == 8) { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 8, 1, in, of, mk, wp, go, gi, gof, gm) }
+    else { DCN_FUSED_CASES(dcn_fused_bwd_kernel, 4, 1, in, of, mk, wp, go, gi, gof, gm) }
     return DEVIS_MSDA_OK;
 }
 

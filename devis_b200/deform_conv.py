@@ -14,11 +14,12 @@ devis_b200/csrc/deform_conv.cuh); the contractions with ``weight`` are cuBLAS GE
 The input is read channels-last: pass a ``torch.channels_last`` tensor to avoid the layout copy; the result is returned
 as an NCHW view of a channels-last buffer.
 
-Two forms (both hand-written kernels of this library, chosen per layer by ``devis_dcn_fused_lanes``):
-  * fused  -- float32, Cin % 4 == 0, Cout in {1, 2, 4, 8, 16, 32, 64} (the high-resolution half of the mask head): gather
-              and contraction in ONE kernel, the column matrix (9x the input) is never written; backward = one kernel
-              for the data gradients (no grad_cols either) + the weight gradient from columns recomputed in bounded
-              chunks, so nothing of column size is kept between forward and backward;
+Two forms (both hand-written kernels of this library, chosen per layer by ``devis_dcn_fused_form``):
+  * fused  -- float32, Cin % 4 == 0, few output channels (the high-resolution half of the mask head; exact rule:
+              devis_dcn_fused_form): gather and contraction in ONE kernel, the column matrix (9x the input) is never
+              written; backward = one kernel for the data gradients when Cout <= 16 (no grad_cols either; wider layers
+              take the grad_cols GEMM + scatter kernel) + the weight gradient from columns recomputed in bounded chunks,
+              so nothing of column size is kept between forward and backward;
   * im2col -- everything else: column matrix + cuBLAS GEMM, as torchvision does.
 ``set_fused(False)`` forces the im2col form (A/B tests).
 
@@ -57,10 +58,11 @@ def set_fused(enabled):
     return old
 
 
-def _fused_lanes(c, cout, dtype):
+def _fused_form(c, cout, kh, kw, dtype):
+    """bit 0: fused forward kernel serves the layer, bit 1: fused data-backward kernel does (devis_dcn_fused_form)"""
     if not _FUSED or dtype != torch.float32:
         return 0
-    return int(_lib.load().devis_dcn_fused_lanes(c, cout, _lib.F32))
+    return int(_lib.load().devis_dcn_fused_form(c, cout, kh, kw, _lib.F32))
 
 
 def _packed_weight(weight):
@@ -105,6 +107,8 @@ class FusedDeformConv2dFunction(Function):
                                                            _ptr(out), *dims, cout,
                                                            torch.cuda.current_stream().cuda_stream))
         ctx.dims, ctx.cout, ctx.has_bias = dims, cout, bias is not None
+        ctx.form = _fused_form(c, cout, kh, kw, input.dtype)
+        ctx.weight = weight.detach() if not ctx.form & 2 else None    # only the GEMM route of the backward reads it
         ctx.save_for_backward(x, offset, mask, packed)
         return out.permute(0, 3, 1, 2)
 
@@ -125,8 +129,22 @@ class FusedDeformConv2dFunction(Function):
                 gx = torch.empty_like(x) if need_in else None
                 grad_off = torch.empty_like(offset)
                 grad_m = torch.empty_like(mask) if mask is not None else None
-                _lib.check(lib.devis_dcn_fused_backward(_ptr(x), _ptr(offset), _ptr(mask), _ptr(packed), _ptr(g), _ptr(gx),
-                                                        _ptr(grad_off), _ptr(grad_m), *ctx.dims, cout, stream))
+                if ctx.form & 2:
+                    _lib.check(lib.devis_dcn_fused_backward(_ptr(x), _ptr(offset), _ptr(mask), _ptr(packed), _ptr(g), _ptr(gx),
+                                                            _ptr(grad_off), _ptr(grad_m), *ctx.dims, cout, stream))
+                else:
+                    # wider layers: column gradient by GEMM (a bounded chunk of the batch at a time) + scatter kernel
+                    w2 = ctx.weight.permute(0, 2, 3, 1).reshape(cout, k * c)
+                    per = max(1, min(n, _COLS_CHUNK_BYTES // max(1, ho * wo * k * c * 4)))
+                    g2 = g.view(n * ho * wo, cout)
+                    for n0 in range(0, n, per):
+                        n1 = min(n, n0 + per)
+                        grad_cols = g2[n0 * ho * wo:n1 * ho * wo] @ w2
+                        _lib.check(lib.devis_dcn_col2im(_ptr(x[n0:n1]), _ptr(offset[n0:n1]),
+                                                        _ptr(mask[n0:n1]) if mask is not None else None, _ptr(grad_cols),
+                                                        _ptr(gx[n0:n1]) if need_in else None, _ptr(grad_off[n0:n1]),
+                                                        _ptr(grad_m[n0:n1]) if mask is not None else None, n1 - n0,
+                                                        *ctx.dims[1:], _DTYPES[x.dtype], stream))
                 grad_in = gx.permute(0, 3, 1, 2) if need_in else None
             if need_w:
                 # cols^T x grad_out from columns recomputed a bounded chunk of the batch at a time
@@ -231,6 +249,6 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     elif out_dtype not in _DTYPES:
         raise RuntimeError(f'"deform_conv2d" not implemented for \'{out_dtype}\'')
     same = lambda t: None if t is None else (t if t.dtype == input.dtype else t.to(input.dtype))
-    fn = FusedDeformConv2dFunction if n > 0 and _fused_lanes(c, cout, input.dtype) else DeformConv2dFunction
+    fn = FusedDeformConv2dFunction if n > 0 and _fused_form(c, cout, kh, kw, input.dtype) & 1 else DeformConv2dFunction
     out = fn.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
     return out if out.dtype == out_dtype else out.to(out_dtype)

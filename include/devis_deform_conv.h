@@ -46,18 +46,21 @@ int devis_dcn_col2im(const void *input_nhwc, const void *offset, const void *mas
 /* ---- fused form: gather + contraction with the weights in one kernel; the column matrix is never written ------------
  * For layers with few output channels (the high-resolution half of the mask head) im2col + GEMM is bound by writing and
  * re-reading columns 9x the size of the input.  The fused kernels read input, offsets, mask once and write the output
- * once.  float only; channels % 4 == 0; out_channels in {1, 2, 4, 8, 16, 32, 64}.
+ * once.  float only; channels % 4 == 0.
  *
- * devis_dcn_fused_lanes: lanes per output pixel of the kernel serving (channels, out_channels), or 0 if the fused form
- * does not serve that layer (use devis_dcn_im2col + GEMM).
- * devis_dcn_pack_weight: rearranges torchvision's weight (out_channels, channels, kh, kw) into the layout the fused
+ * devis_dcn_fused_form: bit 0 set = devis_dcn_fused_forward serves the layer, bit 1 set = devis_dcn_fused_backward does
+ * (0: use devis_dcn_im2col / devis_dcn_col2im + GEMM).  Forward: out_channels in {1, 2, 4, 8, 16} (lane-group kernel) or
+ * a multiple of 16 up to 64 with kh*kw*channels <= 1024 (weights held in the constant bank, 16 output channels per
+ * launch; calls from different streams are ordered against each other on the device because they share that bank).
+ * Backward (data gradients): out_channels in {1, 2, 4, 8, 16}.
+ * devis_dcn_pack_weight: rearranges torchvision's weight (out_channels, channels, kh, kw) into the layouts the fused
  * kernels read (devis_dcn_packed_weight_elems floats; deform_conv.cuh "PACKED WEIGHTS").
  * devis_dcn_fused_forward: out[(n*Ho + ho)*Wo + wo][co] (channels-last, (N, Ho, Wo, out_channels)) = bias[co] +
  *   sum_{k, c} weight[co][c][k] * mask[k] * bilinear(input[n, :, :, c], sample point k); bias may be NULL.
  * devis_dcn_fused_backward: data gradients from grad_out (channels-last like out) without materialising grad_cols:
  *   grad_input_nhwc (zero-filled here, then accumulated; may be NULL), grad_offset, grad_mask (fully written).
  *   The weight gradient is cols^T x grad_out: devis_dcn_im2col + GEMM on the caller's side. */
-int devis_dcn_fused_lanes(int channels, int out_channels, int dtype);
+int devis_dcn_fused_form(int channels, int out_channels, int kernel_h, int kernel_w, int dtype);
 size_t devis_dcn_packed_weight_elems(int channels, int out_channels, int kernel_h, int kernel_w);
 int devis_dcn_pack_weight(const void *weight_oihw, void *packed, int channels, int out_channels, int kernel_h,
                           int kernel_w, void *stream);

@@ -410,6 +410,7 @@ def make_dcn_fixtures(seg):
         "dcn_fused_c40_o64": (1, 40, 64, 4, 5, 3, 1, 1, 1, True, 1.0),
         "dcn_fused_c20_o2": (1, 20, 2, 5, 4, 3, 1, 1, 1, False, 2.0),
         "dcn_fused_c136_o8_k1": (1, 136, 8, 4, 4, 1, 1, 0, 1, True, 0.8),
+        "dcn_fused_c16_o16_s2": (1, 16, 16, 21, 71, 3, 2, 2, 2, False, 1.0),   # constant-bank kernel: 2 x 2 tiles, stride / dilation
     }
     for name, (n, cin, cout, h, w, k, st, pd, dl, use_mask, osc) in cases.items():
         ho = (h + 2 * pd - (dl * (k - 1) + 1)) // st + 1

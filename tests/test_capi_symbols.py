@@ -64,10 +64,12 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.devis_dcn_col2im(null, null, null, null, null, null, null, *dims, 0, null) == -1
     assert lib.devis_dcn_im2col(null, null, null, null, *((0,) + dims[1:]), 0, null) == 0
     # fused form: which layers it serves, packed-weight size, validation order
-    assert lib.devis_dcn_fused_lanes(32, 16, 0) == 8 and lib.devis_dcn_fused_lanes(16, 1, 0) == 4
-    assert lib.devis_dcn_fused_lanes(72, 32, 0) == 8 and lib.devis_dcn_fused_lanes(264, 128, 0) == 0
-    assert lib.devis_dcn_fused_lanes(30, 16, 0) == 0 and lib.devis_dcn_fused_lanes(32, 16, 1) == 0
-    assert lib.devis_dcn_packed_weight_elems(72, 32, 3, 3) == 9 * 3 * 32 * 8 * 4
+    assert lib.devis_dcn_fused_form(32, 16, 3, 3, 0) == 3 and lib.devis_dcn_fused_form(16, 1, 3, 3, 0) == 3
+    assert lib.devis_dcn_fused_form(72, 32, 3, 3, 0) == 1 and lib.devis_dcn_fused_form(264, 128, 3, 3, 0) == 0
+    assert lib.devis_dcn_fused_form(136, 64, 3, 3, 0) == 0 and lib.devis_dcn_fused_form(136, 8, 3, 3, 0) == 3
+    assert lib.devis_dcn_fused_form(30, 16, 3, 3, 0) == 0 and lib.devis_dcn_fused_form(32, 16, 3, 3, 1) == 0
+    assert lib.devis_dcn_packed_weight_elems(72, 32, 3, 3) == 9 * 72 * 32                       # constant layout only
+    assert lib.devis_dcn_packed_weight_elems(32, 16, 3, 3) == 9 * 1 * 16 * 8 * 4 + 9 * 32 * 16   # both layouts
     assert lib.devis_dcn_packed_weight_elems(72, 5, 3, 3) == 0
     assert lib.devis_dcn_pack_weight(null, null, 72, 5, 3, 3, null) == -8
     assert lib.devis_dcn_pack_weight(null, null, 72, 32, 3, 3, null) == -1

@@ -100,7 +100,7 @@ def test_temporal_tables_match_reference_transformer():
 
 DCN_CASES = ["dcn_k3_mask", "dcn_k3_c24", "dcn_k3_c40", "dcn_stride2_dil2_nomask", "dcn_k1", "dcn_c33",
              "dcn_fused_c32_o16", "dcn_fused_c72_o32", "dcn_fused_c16_o1", "dcn_fused_c8_o4_s2", "dcn_fused_c40_o64",
-             "dcn_fused_c20_o2", "dcn_fused_c136_o8_k1"]
+             "dcn_fused_c20_o2", "dcn_fused_c136_o8_k1", "dcn_fused_c16_o16_s2"]
 
 
 def _dcn_run(fn, g, dtype=torch.float64):
