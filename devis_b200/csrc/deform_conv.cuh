@@ -550,28 +550,34 @@ constexpr int kDcnConstFloats = 16384;                 // 64 KB
 __constant__ __align__(16) float dcn_cw[kDcnConstFloats];            // [k][c][16] of the current 16-channel tile
 constexpr int kDcnCTileW = 32, kDcnCTileH = 8, kDcnCStride = kDcnCTileW * kDcnCTileH + 1;
 
-// packed layout for this form: wc[((t * K + k) * C + c) * 16 + q] = weight[16 t + q][c][k]
+// packed layout for this form: wc[((t * K + k) * C + c) * CT + q] = weight[CT t + q][c][k], CT = output channels per thread
 __global__ void dcn_pack_weight_const_kernel(const float *__restrict__ w /* (Cout, C, K) */, float *__restrict__ wc, int cout,
-                                             int C, int K)
+                                             int C, int K, int CT)
 {
     const int total = cout * C * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int q = i & 15;
-        int r = i >> 4;
+        const int q = i % CT;
+        int r = i / CT;
         const int c = r % C;
         r /= C;
         const int k = r % K, t = r / K;
-        wc[i] = w[((long long)(16 * t + q) * C + c) * K + k];
+        wc[i] = w[((long long)(CT * t + q) * C + c) * K + k];
     }
 }
 
-template <int C>
-__global__ void __launch_bounds__(256, 3) dcn_fusedc_fwd_kernel(const float *__restrict__ input, const float *__restrict__ offset,
-                                                                const float *__restrict__ mask, const float *__restrict__ bias,
-                                                                float *__restrict__ out, DcnDims d, int n_base, int cout,
-                                                                int co0)
+// One launch covers kernel positions [k0, k1) for output channels [co0, co0 + CT); the constant bank holds
+// W[k0..k1)[c][CT].  k0 > 0: the partial sums of the earlier positions are read back from `out` (layers whose weights
+// exceed the bank are served by several launches over k; the gathers are not repeated).
+template <int C, int CT>
+__global__ void __launch_bounds__(256, CT == 16 ? 3 : 2)
+    dcn_fusedc_fwd_kernel(const float *__restrict__ input, const float *__restrict__ offset, const float *__restrict__ mask,
+                          const float *__restrict__ bias, float *__restrict__ out, DcnDims d, int n_base, int cout, int co0,
+                          int k0, int k1)
 {
-    extern __shared__ float cols_s[];                  // [C][kDcnCStride]
+    extern __shared__ float4 dcn_smem4[];
+    float *cols_s = reinterpret_cast<float *>(dcn_smem4);                    // [C][kDcnCStride]
+    float4 *rec_f = dcn_smem4 + (C * kDcnCStride + 3) / 4;                   // [8 warps][32 taps] corner factors
+    int4 *rec_r = reinterpret_cast<int4 *>(rec_f + 256);                     // [8 warps][32 taps] corner rows (x C/4)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 7, grp = lane >> 3;
     const int n = n_base + (int)blockIdx.z;
     const int ty0 = (int)blockIdx.y * kDcnCTileH, tx0 = (int)blockIdx.x * kDcnCTileW;
@@ -582,45 +588,60 @@ __global__ void __launch_bounds__(256, 3) dcn_fusedc_fwd_kernel(const float *__r
     const float *offset_n = offset + (long long)n * 2 * K * plane;
     const float *mask_n = mask ? mask + (long long)n * K * plane : nullptr;
 
-    // gather role: this group serves tile pixels p = it * 32 + warp * 4 + grp, it = 0..7 (row it, column warp*4+grp);
-    // lane j of the group fetches the sampling point of the group's j-th pixel and hands it over by shuffle
+    // gather role: the group (warp, grp) serves tile column warp*4+grp, rows it = 0..7.  The 32 taps of a warp and
+    // kernel position are prepared ONCE, one per lane (lane = grp*8 + row), and handed to the groups through shared
+    // memory as two 16-byte records (corner factors with the mask folded in; corner rows).
     const int gx = tx0 + warp * 4 + grp;
-    const int my_y = ty0 + j;                            // pixel whose offsets this lane fetches
+    const int my_y = ty0 + j;
     const bool my_live = my_y < d.Ho && gx < d.Wo;
     const long long my_at = (long long)min(my_y, d.Ho - 1) * d.Wo + min(gx, d.Wo - 1);
-    // contract role: thread owns tile pixel threadIdx.x = row (threadIdx.x / 32), column lane
-    float acc[16];
+    // contract role: thread owns tile pixel threadIdx.x = row warp, column lane
+    const int oy = ty0 + warp, ox = tx0 + lane;
+    const bool out_live = oy < d.Ho && ox < d.Wo;
+    float *o = out + ((long long)n * plane + (long long)min(oy, d.Ho - 1) * d.Wo + min(ox, d.Wo - 1)) * cout + co0;
+    float acc[CT];
+    if (k0 > 0 && out_live) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+        for (int q = 0; q < CT / 4; ++q) {
+            const float4 v = reinterpret_cast<const float4 *>(o)[q];
+            acc[4 * q] = v.x, acc[4 * q + 1] = v.y, acc[4 * q + 2] = v.z, acc[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < CT; ++q) acc[q] = 0.f;
+    }
 
-    DcnPoint nxt = dcn_load_point(offset_n, mask_n, 0, plane, my_at);
+    DcnPoint nxt = dcn_load_point(offset_n, mask_n, k0, plane, my_at);
     int wbase = 0;     // its own induction variable: untouched by the divergent gather code, it stays in a uniform register
-    for (int k = 0; k < K; ++k, wbase += C * 4) {
+    for (int k = k0; k < k1; ++k, wbase += C * (CT / 4)) {
         const int ky = k / d.kw, kx = k - ky * d.kw;
-        const DcnPoint cur = nxt;
-        if (k + 1 < K) nxt = dcn_load_point(offset_n, mask_n, k + 1, plane, my_at);
-        if (k > 0) __syncthreads();                      // everyone is done reading the previous position's columns
+        {
+            const float h = (float)(my_y * d.sh - d.ph + ky * d.dh) + nxt.oh;
+            const float w = (float)(gx * d.sw - d.pw + kx * d.dw) + nxt.ow;
+            const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
+            const float m = nxt.m;
+            if (k + 1 < k1) nxt = dcn_load_point(offset_n, mask_n, k + 1, plane, my_at);
+            rec_f[warp * 32 + lane] = make_float4(m * t.w[0], m * t.w[1], m * t.w[2], m * t.w[3]);
+            rec_r[warp * 32 + lane] = make_int4(my_live ? t.row[0] * C4 : -1, t.row[1] * C4, t.row[2] * C4, t.row[3] * C4);
+        }
+        if (k > k0) __syncthreads();                     // everyone is done reading the previous position's columns
+        else __syncwarp();
 #pragma unroll 2
         for (int it = 0; it < kDcnCTileH; ++it) {
-            const float oh = __shfl_sync(0xffffffffu, cur.oh, it, 8), ow = __shfl_sync(0xffffffffu, cur.ow, it, 8);
-            const float m = __shfl_sync(0xffffffffu, cur.m, it, 8);
-            const bool live = __shfl_sync(0xffffffffu, (int)my_live, it, 8) != 0;
-            if (!live) continue;                         // uniform per group; dead pixels' columns are never read
-            const float h = (float)((ty0 + it) * d.sh - d.ph + ky * d.dh) + oh;
-            const float w = (float)(gx * d.sw - d.pw + kx * d.dw) + ow;
-            const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
-            const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
-            const float4 *r0 = img + t.row[0] * C4, *r1 = img + t.row[1] * C4, *r2 = img + t.row[2] * C4, *r3 = img + t.row[3] * C4;
+            const int4 rr = rec_r[warp * 32 + grp * 8 + it];
+            if (rr.x < 0) continue;                      // pixel outside the plane: its columns are never read
+            const float4 ff = rec_f[warp * 32 + grp * 8 + it];
+            const float4 *r0 = img + rr.x, *r1 = img + rr.y, *r2 = img + rr.z, *r3 = img + rr.w;
             float *dst = cols_s + it * 32 + warp * 4 + grp;
 #pragma unroll
             for (int b = 0; b < nblk; ++b) {
                 const int c = b * 8 + j;
                 if (c >= C4) break;
                 const float4 a = __ldg(r0 + c), bb = __ldg(r1 + c), e = __ldg(r2 + c), f = __ldg(r3 + c);
-                dst[(4 * c + 0) * kDcnCStride] = f0 * a.x + f1 * bb.x + f2 * e.x + f3 * f.x;
-                dst[(4 * c + 1) * kDcnCStride] = f0 * a.y + f1 * bb.y + f2 * e.y + f3 * f.y;
-                dst[(4 * c + 2) * kDcnCStride] = f0 * a.z + f1 * bb.z + f2 * e.z + f3 * f.z;
-                dst[(4 * c + 3) * kDcnCStride] = f0 * a.w + f1 * bb.w + f2 * e.w + f3 * f.w;
+                dst[(4 * c + 0) * kDcnCStride] = ff.x * a.x + ff.y * bb.x + ff.z * e.x + ff.w * f.x;
+                dst[(4 * c + 1) * kDcnCStride] = ff.x * a.y + ff.y * bb.y + ff.z * e.y + ff.w * f.y;
+                dst[(4 * c + 2) * kDcnCStride] = ff.x * a.z + ff.y * bb.z + ff.z * e.z + ff.w * f.z;
+                dst[(4 * c + 3) * kDcnCStride] = ff.x * a.w + ff.y * bb.w + ff.z * e.w + ff.w * f.w;
             }
         }
         __syncthreads();
@@ -633,8 +654,8 @@ __global__ void __launch_bounds__(256, 3) dcn_fusedc_fwd_kernel(const float *__r
         for (int c = 0; c < C; ++c) {
             const float v = col[c * kDcnCStride];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 w4 = wk[c * 4 + q];
+            for (int q = 0; q < CT / 4; ++q) {
+                const float4 w4 = wk[c * (CT / 4) + q];
                 acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
                 acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
                 acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
@@ -642,16 +663,15 @@ __global__ void __launch_bounds__(256, 3) dcn_fusedc_fwd_kernel(const float *__r
             }
         }
     }
-    const int oy = ty0 + warp, ox = tx0 + lane;
-    if (oy >= d.Ho || ox >= d.Wo) return;
-    float4 *o = reinterpret_cast<float4 *>(out + ((long long)n * plane + (long long)oy * d.Wo + ox) * cout + co0);
+    if (!out_live) return;
+    const bool last = k1 == K;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < CT / 4; ++q) {
         float4 v = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-        if (bias) {
+        if (bias && last) {
             v.x += bias[co0 + 4 * q], v.y += bias[co0 + 4 * q + 1], v.z += bias[co0 + 4 * q + 2], v.w += bias[co0 + 4 * q + 3];
         }
-        o[q] = v;
+        reinterpret_cast<float4 *>(o)[q] = v;
     }
 }
 

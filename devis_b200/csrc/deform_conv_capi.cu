@@ -131,6 +131,7 @@ struct FusedPlan {
     bool lanes_fwd = false;    // forward by dcn_fused_fwd_kernel
     bool lanes_bwd = false;    // data backward by dcn_fused_bwd_kernel
     bool constant = false;     // forward by dcn_fusedc_fwd_kernel (weights in the constant bank)
+    int CT = 16;               // its output channels per thread
     size_t lanes_elems = 0, const_elems = 0;   // packed buffer = [lane-group layout | constant layout]
     bool any() const { return lanes_fwd || lanes_bwd || constant; }
 };
@@ -142,8 +143,9 @@ FusedPlan fused_plan(int C, int cout, int kh, int kw, int dtype)
     const long long K = (long long)kh * kw;
     const bool small = cout == 1 || cout == 2 || cout == 4 || cout == 8 || cout == 16;
     p.G = C / 4 > 4 ? 8 : 4;
-    const bool c_served = C == 16 || C == 32 || C == 40 || C == 64 || C == 72;   // dcn_fusedc_fwd_kernel<C> instantiations
-    p.constant = c_served && cout % 16 == 0 && cout <= 64 && K * C * 16 <= kDcnConstFloats;
+    const bool c_served = C == 16 || C == 32 || C == 40 || C == 64 || C == 72;   // dcn_fusedc_fwd_kernel<C, CT> instantiations
+    p.constant = c_served && cout % 16 == 0 && cout <= 64;
+    p.CT = cout % 32 == 0 ? 32 : 16;
     p.lanes_bwd = small;
     p.lanes_fwd = small && !p.constant;
     if (p.lanes_fwd || p.lanes_bwd) p.lanes_elems = (size_t)K * ((C / 4 + p.G - 1) / p.G) * cout * p.G * 4;
@@ -156,7 +158,7 @@ FusedPlan fused_plan(int C, int cout, int kh, int kw, int dtype)
 std::mutex g_const_mutex;
 cudaEvent_t g_const_event = nullptr;
 cudaStream_t g_const_stream = nullptr;
-bool g_const_used = false, g_const_attr = false;
+bool g_const_used = false;
 
 bool stream_is_capturing(cudaStream_t st)
 {
@@ -204,7 +206,7 @@ int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int ou
     if (p.const_elems) {
         const unsigned blocks = (unsigned)((p.const_elems + 255) / 256 > 1184 ? 1184 : (p.const_elems + 255) / 256);
         dcn_pack_weight_const_kernel<<<blocks, 256, 0, st>>>((const float *)weight, (float *)packed + p.lanes_elems,
-                                                             out_channels, channels, K);
+                                                             out_channels, channels, K, p.CT);
         const int rc = devis_capi_check_launch();
         if (rc) return rc;
     }
@@ -251,19 +253,21 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
     float *o = (float *)out;
     if (plan.constant) {
         const float *wc = (const float *)packed_weight + plan.lanes_elems;
-        const size_t tile_floats = (size_t)kernel_h * kernel_w * channels * 16;
-        const size_t smem = (size_t)channels * kDcnCStride * sizeof(float);
+        const int K = kernel_h * kernel_w, CT = plan.CT;
+        const int k_fit = kDcnConstFloats / (channels * CT);                    // kernel positions the bank holds
+        const int n_chunks = (K + k_fit - 1) / k_fit, k_step = (K + n_chunks - 1) / n_chunks;
+        const size_t smem = (((size_t)channels * kDcnCStride + 3) / 4 + 512) * 16;
+        typedef void (*Kernel)(const float *, const float *, const float *, const float *, float *, DcnDims, int, int, int, int, int);
+        Kernel kernel = nullptr;
+#define DCN_CONST_PICK(CC)                                                                  \
+        if (channels == CC) kernel = CT == 16 ? (Kernel)dcn_fusedc_fwd_kernel<CC, 16> : (Kernel)dcn_fusedc_fwd_kernel<CC, 32>;
+        DCN_CONST_PICK(16) DCN_CONST_PICK(32) DCN_CONST_PICK(40) DCN_CONST_PICK(64) DCN_CONST_PICK(72)
+#undef DCN_CONST_PICK
+        if (!kernel) return DEVIS_MSDA_ERR_UNSUPPORTED;
         std::lock_guard<std::mutex> lock(g_const_mutex);
-        void (*kernel)(const float *, const float *, const float *, const float *, float *, DcnDims, int, int, int) =
-            channels == 16 ? dcn_fusedc_fwd_kernel<16> : channels == 32 ? dcn_fusedc_fwd_kernel<32> :
-            channels == 40 ? dcn_fusedc_fwd_kernel<40> : channels == 64 ? dcn_fusedc_fwd_kernel<64> : dcn_fusedc_fwd_kernel<72>;
-        if (!g_const_attr) {
-            cudaError_t e = cudaSuccess;
-            const int most = 72 * kDcnCStride * (int)sizeof(float);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(dcn_fusedc_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(dcn_fusedc_fwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        {
+            const cudaError_t e = cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return devis_capi_cuda_fail(e);
-            g_const_attr = true;
         }
         const bool capturing = stream_is_capturing(st);
         if (!capturing) {
@@ -276,16 +280,20 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
                 if (e != cudaSuccess) return devis_capi_cuda_fail(e);
             }
         }
-        for (int t = 0; t < out_channels / 16; ++t) {
-            const cudaError_t e = cudaMemcpyToSymbolAsync(dcn_cw, wc + t * tile_floats, tile_floats * sizeof(float), 0,
-                                                          cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
-            for (int n0 = 0; n0 < d.N; n0 += kMaxGridZ) {
-                const dim3 grid((unsigned)((d.Wo + kDcnCTileW - 1) / kDcnCTileW), (unsigned)((d.Ho + kDcnCTileH - 1) / kDcnCTileH),
-                                (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));
-                kernel<<<grid, 256, smem, st>>>(in, of, mk, bs, o, d, n0, out_channels, 16 * t);
-                const int rc_ = devis_capi_check_launch();
-                if (rc_) return rc_;
+        for (int t = 0; t < out_channels / CT; ++t) {
+            for (int k0 = 0; k0 < K; k0 += k_step) {
+                const int k1 = k0 + k_step < K ? k0 + k_step : K;
+                const cudaError_t e = cudaMemcpyToSymbolAsync(dcn_cw, wc + ((size_t)t * K + k0) * channels * CT,
+                                                              (size_t)(k1 - k0) * channels * CT * sizeof(float), 0,
+                                                              cudaMemcpyDeviceToDevice, st);
+                if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+                for (int n0 = 0; n0 < d.N; n0 += kMaxGridZ) {
+                    const dim3 grid((unsigned)((d.Wo + kDcnCTileW - 1) / kDcnCTileW), (unsigned)((d.Ho + kDcnCTileH - 1) / kDcnCTileH),
+                                    (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));
+                    kernel<<<grid, 256, smem, st>>>(in, of, mk, bs, o, d, n0, out_channels, CT * t, k0, k1);
+                    const int rc_ = devis_capi_check_launch();
+                    if (rc_) return rc_;
+                }
             }
         }
         if (!capturing) {
