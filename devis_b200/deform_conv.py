@@ -249,6 +249,10 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     elif out_dtype not in _DTYPES:
         raise RuntimeError(f'"deform_conv2d" not implemented for \'{out_dtype}\'')
     same = lambda t: None if t is None else (t if t.dtype == input.dtype else t.to(input.dtype))
-    fn = FusedDeformConv2dFunction if n > 0 and _fused_form(c, cout, kh, kw, input.dtype) & 1 else DeformConv2dFunction
+    # fused forward when the layer is served; when gradients are needed only if its data backward is fused as well
+    # (otherwise the im2col form, which keeps its columns for the backward, is the faster training path)
+    form = _fused_form(c, cout, kh, kw, input.dtype) if n > 0 else 0
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (input, offset, weight, bias, mask))
+    fn = FusedDeformConv2dFunction if form & 1 and (form & 2 or not needs_grad) else DeformConv2dFunction
     out = fn.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
     return out if out.dtype == out_dtype else out.to(out_dtype)
