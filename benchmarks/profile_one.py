@@ -19,6 +19,9 @@ ap.add_argument("--tile", default="8x8")
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--qpg", type=int, default=0)
 ap.add_argument("--sigma", type=float, default=2.0)
+ap.add_argument("--bwd-mode", type=int, default=0, help="tuning key 6: 1 direct scatter, 2 windowed, 3 sorted")
+ap.add_argument("--margin", type=int, default=0)
+ap.add_argument("--min-level", type=int, default=0)
 a = ap.parse_args()
 clip = synthetic.make_clip(dist=a.dist, dtype={"fp32": torch.float32, "bf16": torch.bfloat16}[a.dtype], device="cuda", sigma_px=a.sigma)
 geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
@@ -27,6 +30,9 @@ rc = RawClip(clip, order)
 for k in (0, 2):
     _lib.set_tuning(k, a.threads)
     _lib.set_tuning(k + 1, a.qpg)
+_lib.set_tuning(6, a.bwd_mode)
+_lib.set_tuning(7, a.margin)
+_lib.set_tuning(9, a.min_level)
 for _ in range(a.iters):
     rc.fwd() if a.kind == "fwd" else rc.bwd()
 torch.cuda.synchronize()

@@ -9,6 +9,7 @@
 #include "../../include/devis_msda.h"
 #include "msda_bwd.cuh"
 #include "msda_bwd_win.cuh"
+#include "msda_bwd_sort.cuh"
 #include "msda_common.cuh"
 #include "msda_fwd.cuh"
 #include "msda_generic.cuh"
@@ -351,6 +352,63 @@ int launch_backward_window(const BwdArgs<ClipTable> &a, int dtype, void *workspa
     return check_launch();
 }
 
+// ---- sorted whole-clip backward (msda_bwd_sort.cuh) ---------------------------------------------------------------
+// Serves the encoder form: one query per pyramid pixel (the caller says so by passing a query_order), D = 32, fp32 /
+// bf16 value with float grad_value, levels stored back to back, an even number of levels, 4 points per slot.  Tuning
+// key 6: 3 = on, 1 = off (0 = library default); key 7 = window margin in pixels (default 6); key 9 = first level with a
+// window + 1 (default: all levels).
+bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags)
+{
+    const int mode = g_tuning[6].load();
+    if (mode != 3) return false;
+    if (!a.q_perm || !a.grad_value || (flags & (DEVIS_MSDA_FLAG_DETERMINISTIC | DEVIS_MSDA_FLAG_BF16_GRAD_VALUE))) return false;
+    if (lanes_per_group(dtype, a.d) != 8 || a.d.Lq != a.d.S || a.d.outer == 0) return false;
+    const ClipTable &tb = a.src;
+    if (tb.L % 2 != 0) return false;
+    int next = 0;
+    for (int l = 0; l < tb.L; ++l) {
+        if (tb.lsi[l] != next || tb.H[l] * (long long)tb.W[l] > 65536) return false;
+        next += tb.H[l] * tb.W[l];
+    }
+    if (next != a.d.S) return false;
+    for (int sg = 0; sg < a.n_seg; ++sg)
+        if (a.seg[sg].P != 4 || a.seg[sg].n_slots % tb.L != 0) return false;
+    return true;
+}
+
+int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, cudaStream_t st)
+{
+    const OpDims &d = a.d;
+    SortArgs w{};
+    w.b = a;
+    int tiles = 0;
+    for (int l = 0; l < a.src.L; ++l) {
+        w.tiles_x[l] = (a.src.W[l] + kSortTile - 1) / kSortTile;
+        w.tile_start[l] = tiles;
+        tiles += w.tiles_x[l] * ((a.src.H[l] + kSortTile - 1) / kSortTile);
+    }
+    w.n_tiles = tiles;
+    w.margin = g_tuning[7].load() > 0 ? g_tuning[7].load() : 6;
+    w.min_level = g_tuning[9].load() > 0 ? g_tuning[9].load() - 1 : 0;
+    w.lut_entries = (a.src.L / 2) * kSortMaxKeys;
+    cudaError_t e = cudaMemsetAsync(a.grad_value, 0, (size_t)d.outer * d.S * d.M * d.D * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e);
+    const size_t smem = sort_smem_bytes(a.n_slots_total, w.lut_entries);
+    if (smem > 200 * 1024) return DEVIS_MSDA_ERR_TOO_LARGE;
+    if ((long long)tiles * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+    const dim3 grid((unsigned)(tiles * d.M), (unsigned)d.outer);
+    if (dtype == DEVIS_MSDA_BF16) {
+        e = cudaFuncSetAttribute(msda_bwds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        msda_bwds_kernel<true><<<grid, kSortThreads, smem, st>>>(w);
+    } else {
+        e = cudaFuncSetAttribute(msda_bwds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        msda_bwds_kernel<false><<<grid, kSortThreads, smem, st>>>(w);
+    }
+    return check_launch();
+}
+
 int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
 {
     if (dtype != DEVIS_MSDA_F32 && dtype != DEVIS_MSDA_F64 && dtype != DEVIS_MSDA_BF16) return DEVIS_MSDA_ERR_BAD_DTYPE;
@@ -563,6 +621,7 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
     a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
     a.q_perm = query_order;
+    if (sort_applicable(a, dtype, flags)) return launch_backward_sort(a, dtype, (cudaStream_t)stream);
     if (window_applicable(a, dtype, flags, workspace, workspace_bytes))
         return launch_backward_window(a, dtype, workspace, (cudaStream_t)stream);
     return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);

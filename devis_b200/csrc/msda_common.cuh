@@ -147,11 +147,14 @@ struct TapExchange {
 
     __device__ static __forceinline__ int rec_word(int j, int g) { return (j * GPW + (g ^ (j & (GPW - 1)))) * 8; }
 
-    __device__ static __forceinline__ void publish(float *buf, int j, int g, const TapGeom &t, float w, unsigned rowbytes)
+    // tag: bit 0 of the TL offset (row pitches are even) -- msda_bwd_sort.cuh marks taps whose grad_value
+    // contributions take the sorted path; every other caller leaves it 0
+    __device__ static __forceinline__ void publish(float *buf, int j, int g, const TapGeom &t, float w, unsigned rowbytes,
+                                                   unsigned tag = 0u)
     {
         const bool live = t.ok != 0u;
         uint4 off;
-        off.x = (unsigned)t.rTL * rowbytes;
+        off.x = ((unsigned)t.rTL * rowbytes) | tag;
         off.y = (unsigned)t.rTR * rowbytes;
         off.z = (unsigned)t.rBL * rowbytes;
         off.w = (unsigned)t.rBR * rowbytes;
