@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                 float2 xy = make_float2(0.f, 0.f);
                 float w = 0.f;
                 if (live) {
-                    xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                    w = __ldg(aw + row * K + k);
+                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                    w = ld_stream_f(aw + row * K + k);
                 }
                 const TapGeom t = tap_geometry(xy.x, xy.y, sl, live);
                 float *buf = xbuf + parity * X::kWordsPerWarpBuf;
@@ -199,9 +199,9 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                     const float val = hh * (hw * A[0] + lw * A[1]) + lh * (hw * A[2] + lw * A[3]);
                     const float gx = hh * (r_in * A[1] - l_in * A[0]) + lh * (r_in * A[3] - l_in * A[2]);
                     const float gy = hw * (b_in * A[2] - t_in * A[0]) + lw * (b_in * A[3] - t_in * A[1]);
-                    gaw[row * K + k] = hit ? val : 0.f;
-                    reinterpret_cast<float2 *>(gloc + row * K * 2)[k] =
-                        hit ? make_float2((float)sl.y * gx * w, (float)sl.x * gy * w) : make_float2(0.f, 0.f);
+                    st_stream_f(gaw + row * K + k, hit ? val : 0.f);
+                    st_stream_f2(reinterpret_cast<float2 *>(gloc + row * K * 2) + k,
+                                 hit ? make_float2((float)sl.y * gx * w, (float)sl.x * gy * w) : make_float2(0.f, 0.f));
                 }
             }
         }

@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256, DEVIS_FWD_MIN_BLOCKS) msda_fwd_kernel(con
                 float2 xy = make_float2(0.f, 0.f);
                 float w = 0.f;
                 if (live) {
-                    xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                    w = __ldg(aw + row * K + k);
+                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                    w = ld_stream_f(aw + row * K + k);
                 }
                 const TapGeom t = tap_geometry(xy.x, xy.y, sl, live);
                 float *buf = xbuf + parity * X::kWordsPerWarpBuf;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, DEVIS_FWD_MIN_BLOCKS) msda_fwd_kernel(con
         if (BF16)
             reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc[i]);
         else
-            reinterpret_cast<float4 *>(a.out)[row * LPG + j] = acc[i];
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row * LPG + j, acc[i]);
     }
 }
 
@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
             in[i].xy = make_float2(0.f, 0.f);
             in[i].w = 0.f;
             if (k < K && qlive[i]) {
-                in[i].xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                in[i].w = __ldg(aw + row * K + k);
+                in[i].xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                in[i].w = ld_stream_f(aw + row * K + k);
             }
         }
     };
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
         if (BF16)
             reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc[i]);
         else
-            reinterpret_cast<float4 *>(a.out)[row * LPG + j] = acc[i];
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row * LPG + j, acc[i]);
     }
 }
 
@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a
                 float2 xy = make_float2(0.f, 0.f);
                 float w = 0.f;
                 if (qlive[i]) {
-                    xy = __ldg(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                    w = __ldg(aw + row * K + k);
+                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                    w = ld_stream_f(aw + row * K + k);
                 }
                 const TapGeom t = tap_geometry(xy.x, xy.y, sl, qlive[i]);
                 uint4 rec;
