@@ -57,7 +57,11 @@ __host__ __device__ inline size_t sort_smem_bytes(int n_slots_total, int lut_ent
            2 * (size_t)kSortMaxKeys * 4 + 2 * (size_t)kSortRecords * 8 + (((size_t)lut_entries * 2 + 15) & ~(size_t)15);
 }
 
-template <bool BF16>
+// DET (DEVIS_MSDA_FLAG_DETERMINISTIC): every contribution is converted exactly to 64-bit fixed point (the integers
+// msda_bwd_kernel's det_add4 adds, same scale) and both the in-register run sums and the global reductions are integer
+// additions: associative, so the result does not depend on the arrival order of the ranks -- and is bit-identical to
+// the direct deterministic scatter, with 5x fewer 64-bit reductions leaving the SM.
+template <bool BF16, bool DET = false>
 __global__ void __launch_bounds__(kSortThreads, DEVIS_BWDS_MIN_BLOCKS) msda_bwds_kernel(const SortArgs a)
 {
     constexpr int LPG = 8;
@@ -165,9 +169,12 @@ __global__ void __launch_bounds__(kSortThreads, DEVIS_BWDS_MIN_BLOCKS) msda_bwds
     const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
     const char *vbase = reinterpret_cast<const char *>(b.value) + (size_t)(m * LPG + j) * kQuadBytes;
     asm volatile("" : "+l"(vbase));
-    char *gvb = reinterpret_cast<char *>(b.grad_value) + (size_t)(m * LPG + j) * 16u;   // fp32 grad_value (host-checked)
-    constexpr unsigned kGvShift = BF16 ? 1u : 0u;
-    const size_t gv_rowbytes = (size_t)(M * LPG) * 16u;
+    // fp32 grad_value (host-checked), or the deterministic mode's 8-byte accumulators in det_add4's permuted order
+    char *gvb = DET ? reinterpret_cast<char *>(b.det.acc) + (size_t)(m * LPG) * 32u + (size_t)j * 8u
+                    : reinterpret_cast<char *>(b.grad_value) + (size_t)(m * LPG + j) * 16u;
+    constexpr unsigned kGvShift = (BF16 ? 1u : 0u) + (DET ? 1u : 0u);
+    const size_t gv_rowbytes = (size_t)(M * LPG) * (DET ? 32u : 16u);
+    const float det_sh = DET ? ldexpf(1.f, kDetFracBits - det_exponent(b.det.max_bits)) : 0.f;
 
     int slot_base = 0, parity = 0, cp = 0;
     for (int sg = 0; sg < b.n_seg; ++sg) {
@@ -257,10 +264,17 @@ __global__ void __launch_bounds__(kSortThreads, DEVIS_BWDS_MIN_BLOCKS) msda_bwds
                     dsum[jj][2] = fmaf(v10.w, gg.w, fmaf(v10.z, gg.z, fmaf(v10.y, gg.y, v10.x * gg.x)));
                     dsum[jj][3] = fmaf(v11.w, gg.w, fmaf(v11.z, gg.z, fmaf(v11.y, gg.y, v11.x * gg.x)));
                     if (direct) {
-                        if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
-                        if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
-                        if (c.z != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.z << kGvShift)), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
-                        if (c.w != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.w << kGvShift)), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                        if (DET) {
+                            if (c.x != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(gvb + ((size_t)off.x << kGvShift)), det_sh, c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                            if (c.y != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(gvb + ((size_t)off.y << kGvShift)), det_sh, c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                            if (c.z != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(gvb + ((size_t)off.z << kGvShift)), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                            if (c.w != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(gvb + ((size_t)off.w << kGvShift)), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                        } else {
+                            if (c.x != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.x << kGvShift)), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                            if (c.y != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.y << kGvShift)), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                            if (c.z != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.z << kGvShift)), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                            if (c.w != 0.f) red_add_f4(reinterpret_cast<float *>(gvb + ((size_t)off.w << kGvShift)), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                        }
                     }
                 }
 
@@ -332,7 +346,18 @@ __global__ void __launch_bounds__(kSortThreads, DEVIS_BWDS_MIN_BLOCKS) msda_bwds
                 const int n_a = s_lw[5 * (la + 1) + 4] - kb0;        // keys below belong to slot0, the rest to slot0 + 1
                 const int za = s_slot[slot0].z, zb = s_slot[slot0 + 1].z;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                long long ai[4] = {0, 0, 0, 0};
                 int cur = -1;
+                auto flush = [&](int key) {
+                    const size_t vrow = (size_t)((key < n_a ? za : zb) + (int)s_lut[kb0 + key]);
+                    if (DET) {
+                        unsigned long long *p = reinterpret_cast<unsigned long long *>(gvb + vrow * gv_rowbytes);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) atomicAdd(p + c * LPG, (unsigned long long)ai[c]);
+                    } else {
+                        red_add_f4(reinterpret_cast<float *>(gvb + vrow * gv_rowbytes), acc.x, acc.y, acc.z, acc.w);
+                    }
+                };
                 uint2 r = make_uint2(0u, 0u);
                 if (beg < end) r = s_sorted[beg];
                 for (int i = beg; i < end; ++i) {
@@ -340,24 +365,27 @@ __global__ void __launch_bounds__(kSortThreads, DEVIS_BWDS_MIN_BLOCKS) msda_bwds
                     const int key = (int)(r.y >> 6), qq = (int)(r.y & 63u);
                     const float4 gq = reinterpret_cast<const float4 *>(s_go)[qq * LPG + j];
                     if (key != cur) {
-                        if (cur >= 0) {
-                            const size_t vrow = (size_t)((cur < n_a ? za : zb) + (int)s_lut[kb0 + cur]);
-                            red_add_f4(reinterpret_cast<float *>(gvb + vrow * gv_rowbytes), acc.x, acc.y, acc.z, acc.w);
-                        }
+                        if (cur >= 0) flush(cur);
                         acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        ai[0] = ai[1] = ai[2] = ai[3] = 0;
                         cur = key;
                     }
                     const float c = __uint_as_float(r.x);
-                    acc.x = fmaf(c, gq.x, acc.x);
-                    acc.y = fmaf(c, gq.y, acc.y);
-                    acc.z = fmaf(c, gq.z, acc.z);
-                    acc.w = fmaf(c, gq.w, acc.w);
+                    if (DET) {
+                        // the same integers det_add4 adds for the direct path: round(c * g) to float, exact scaling
+                        ai[0] += __float2ll_rn(__fmul_rn(c, gq.x) * det_sh);
+                        ai[1] += __float2ll_rn(__fmul_rn(c, gq.y) * det_sh);
+                        ai[2] += __float2ll_rn(__fmul_rn(c, gq.z) * det_sh);
+                        ai[3] += __float2ll_rn(__fmul_rn(c, gq.w) * det_sh);
+                    } else {
+                        acc.x = fmaf(c, gq.x, acc.x);
+                        acc.y = fmaf(c, gq.y, acc.y);
+                        acc.z = fmaf(c, gq.z, acc.z);
+                        acc.w = fmaf(c, gq.w, acc.w);
+                    }
                     r = rn;
                 }
-                if (cur >= 0) {
-                    const size_t vrow = (size_t)((cur < n_a ? za : zb) + (int)s_lut[kb0 + cur]);
-                    red_add_f4(reinterpret_cast<float *>(gvb + vrow * gv_rowbytes), acc.x, acc.y, acc.z, acc.w);
-                }
+                if (cur >= 0) flush(cur);
             }
             cp ^= 1;
         }

@@ -188,6 +188,12 @@ size_t det_workspace_bytes(long long outer, long long S, long long M, long long 
     return (size_t)(outer * S * M * D) * sizeof(long long) + 16;
 }
 
+// sorted whole-clip backward (msda_bwd_sort.cuh), defined below
+bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, bool det);
+int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, bool det, cudaStream_t st);
+inline bool sort_applicable(const BwdArgs<DeviceLevels> &, int, unsigned, bool) { return false; }
+inline int launch_backward_sort(const BwdArgs<DeviceLevels> &, int, bool, cudaStream_t) { return DEVIS_MSDA_ERR_UNSUPPORTED; }
+
 template <class SlotSrc>
 int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
                     cudaStream_t st)
@@ -239,6 +245,12 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
     };
     if (d.outer == 0 || d.Lq == 0) return finalize();
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
+    if (lpg && det && sort_applicable(a, dtype, flags, true)) {
+        // deterministic mode, encoder form: sorted pre-aggregation in 64-bit fixed point (bit-identical to the direct
+        // deterministic scatter, ~4x faster: 5x fewer 64-bit reductions leave the SM)
+        const int rc = launch_backward_sort(a, dtype, true, st);
+        return rc ? rc : finalize();
+    }
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, kShapeBwd, half_acc ? 1 : 2, 2, 3);
         smem += exchange_bytes(lpg, s.threads);
@@ -354,14 +366,16 @@ int launch_backward_window(const BwdArgs<ClipTable> &a, int dtype, void *workspa
 
 // ---- sorted whole-clip backward (msda_bwd_sort.cuh) ---------------------------------------------------------------
 // Serves the encoder form: one query per pyramid pixel (the caller says so by passing a query_order), D = 32, fp32 /
-// bf16 value with float grad_value, levels stored back to back, an even number of levels, 4 points per slot.  Tuning
-// key 6: 3 = on, 1 = off (0 = library default); key 7 = window margin in pixels (default 6); key 9 = first level with a
-// window + 1 (default: all levels).
-bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags)
+// bf16 value with float grad_value, levels stored back to back, an even number of levels, 4 points per slot.
+// Default mode: slower than the direct scatter (data-pipe bound) -> opt-in, tuning key 6 = 3.
+// Deterministic mode: ~4x faster than the direct 64-bit scatter and bit-identical to it -> on unless key 6 = 1.
+// Key 7 = window margin in pixels (default 6); key 9 = first level with a window + 1 (default: all levels).
+bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, bool det)
 {
     const int mode = g_tuning[6].load();
-    if (mode != 3) return false;
-    if (!a.q_perm || !a.grad_value || (flags & (DEVIS_MSDA_FLAG_DETERMINISTIC | DEVIS_MSDA_FLAG_BF16_GRAD_VALUE))) return false;
+    if (det ? mode == 1 : mode != 3) return false;          // deterministic mode: on by default; else opt-in
+    if (det ? !a.det.acc : (!a.grad_value || (flags & DEVIS_MSDA_FLAG_DETERMINISTIC))) return false;
+    if (!a.q_perm || (flags & DEVIS_MSDA_FLAG_BF16_GRAD_VALUE)) return false;
     if (lanes_per_group(dtype, a.d) != 8 || a.d.Lq != a.d.S || a.d.outer == 0) return false;
     const ClipTable &tb = a.src;
     if (tb.L % 2 != 0) return false;
@@ -373,10 +387,21 @@ bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags)
     if (next != a.d.S) return false;
     for (int sg = 0; sg < a.n_seg; ++sg)
         if (a.seg[sg].P != 4 || a.seg[sg].n_slots % tb.L != 0) return false;
+    if (sort_smem_bytes(a.n_slots_total, (tb.L / 2) * kSortMaxKeys) > 200 * 1024) return false;
     return true;
 }
 
-int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, cudaStream_t st)
+template <bool BF, bool DET>
+int launch_sort_kernel(const SortArgs &w, dim3 grid, size_t smem, cudaStream_t st)
+{
+    const cudaError_t e = cudaFuncSetAttribute(msda_bwds_kernel<BF, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e);
+    msda_bwds_kernel<BF, DET><<<grid, kSortThreads, smem, st>>>(w);
+    return check_launch();
+}
+
+// det: the caller (launch_backward) has set up a.det and zero-filled the accumulators, and runs the finalize pass
+int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, bool det, cudaStream_t st)
 {
     const OpDims &d = a.d;
     SortArgs w{};
@@ -391,22 +416,15 @@ int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, cudaStream_t st
     w.margin = g_tuning[7].load() > 0 ? g_tuning[7].load() : 6;
     w.min_level = g_tuning[9].load() > 0 ? g_tuning[9].load() - 1 : 0;
     w.lut_entries = (a.src.L / 2) * kSortMaxKeys;
-    cudaError_t e = cudaMemsetAsync(a.grad_value, 0, (size_t)d.outer * d.S * d.M * d.D * sizeof(float), st);
-    if (e != cudaSuccess) return cuda_fail(e);
+    if (!det) {
+        const cudaError_t e = cudaMemsetAsync(a.grad_value, 0, (size_t)d.outer * d.S * d.M * d.D * sizeof(float), st);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
     const size_t smem = sort_smem_bytes(a.n_slots_total, w.lut_entries);
-    if (smem > 200 * 1024) return DEVIS_MSDA_ERR_TOO_LARGE;
     if ((long long)tiles * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
     const dim3 grid((unsigned)(tiles * d.M), (unsigned)d.outer);
-    if (dtype == DEVIS_MSDA_BF16) {
-        e = cudaFuncSetAttribute(msda_bwds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e);
-        msda_bwds_kernel<true><<<grid, kSortThreads, smem, st>>>(w);
-    } else {
-        e = cudaFuncSetAttribute(msda_bwds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e);
-        msda_bwds_kernel<false><<<grid, kSortThreads, smem, st>>>(w);
-    }
-    return check_launch();
+    if (dtype == DEVIS_MSDA_BF16) return det ? launch_sort_kernel<true, true>(w, grid, smem, st) : launch_sort_kernel<true, false>(w, grid, smem, st);
+    return det ? launch_sort_kernel<false, true>(w, grid, smem, st) : launch_sort_kernel<false, false>(w, grid, smem, st);
 }
 
 int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
@@ -621,7 +639,7 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
     a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
     a.q_perm = query_order;
-    if (sort_applicable(a, dtype, flags)) return launch_backward_sort(a, dtype, (cudaStream_t)stream);
+    if (sort_applicable(a, dtype, flags, false)) return launch_backward_sort(a, dtype, false, (cudaStream_t)stream);
     if (window_applicable(a, dtype, flags, workspace, workspace_bytes))
         return launch_backward_window(a, dtype, workspace, (cudaStream_t)stream);
     return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -545,3 +545,32 @@ def test_sorted_backward_matches_direct_scatter():
     ref.backward(cpu["grad_out"])
     for got, leaf in zip(grads, leaves):
         assert nmax(got.cpu().numpy(), leaf.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_deterministic_sorted_backward_is_bit_identical_to_direct_deterministic_scatter(dtype):
+    """Deterministic mode in the encoder form (query order given) runs msda_bwds_kernel<DET>: the same 64-bit fixed-point
+    integers as the direct deterministic scatter, pre-summed per row run in registers -- integer addition is associative,
+    so grad_value must be bit-identical to the direct path (tuning key 6 = 1) and identical run to run; full DeVIS shape
+    (local and uniform taps) and a ragged 4-level pyramid."""
+    from devis_b200 import MultiScaleDeformableAttention as MSDA, _lib, clip_geometry, synthetic
+    cases = [dict(dist="local", seed=21), dict(dist="uniform", seed=22),
+             dict(n_frames=4, shapes=((18, 30), (9, 15), (5, 8), (3, 4)), dist="local", seed=23)]
+    MSDA.set_deterministic(True)
+    try:
+        for kw in cases:
+            clip = synthetic.make_clip(device="cuda", dtype=dtype, **kw)
+            geom = clip_geometry.ClipGeometry(clip["shapes"], clip["value"].shape[0], clip["frame_table"])
+            order = geom.tile_order("cuda")
+            _lib.set_tuning(6, 1)
+            _, direct, _ = _clip_fn(clip, order=order)
+            _lib.set_tuning(6, 0)
+            launches = _lib.load().devis_msda_launch_count()
+            _, srt, _ = _clip_fn(clip, order=order)
+            _, again, _ = _clip_fn(clip, order=order)
+            assert _lib.load().devis_msda_launch_count() > launches
+            for a, b, c in zip(srt, direct, again):
+                assert torch.equal(a, b) and torch.equal(a, c), kw
+    finally:
+        _lib.set_tuning(6, 0)
+        MSDA.set_deterministic(False)
