@@ -679,12 +679,13 @@ static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, co
     return DEVIS_MSDA_OK;
 }
 
-static int fused_grid(const FusedArgs &a, int key_threads, dim3 &grid, int &threads, size_t &smem)
+static int fused_grid(const FusedArgs &a, int key_threads, dim3 &grid, int &threads, size_t &smem, int qpg = 1)
 {
     threads = g_tuning[key_threads].load();
     if (threads == 0) threads = a.d.Lq >= 1024 ? (key_threads == 2 ? 128 : 256) : a.d.Lq >= 128 ? 128 : 64;   // see pick_shape
     threads = threads < 32 ? 32 : threads > 256 ? 256 : (threads / 32) * 32;
-    const long long chunks = ((long long)a.d.Lq + threads / 8 - 1) / (threads / 8);
+    const long long per_block = (long long)(threads / 8) * qpg;
+    const long long chunks = ((long long)a.d.Lq + per_block - 1) / per_block;
     if (chunks * a.d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
     grid = dim3((unsigned)(chunks * a.d.M), (unsigned)a.d.outer);
     smem = (size_t)(a.n_slots[0] + a.n_slots[1]) * sizeof(int4) + exchange_bytes(8, threads);
@@ -710,10 +711,32 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
     dim3 grid;
     int threads;
     size_t smem;
-    rc = fused_grid(a, 0, grid, threads, smem);
+    // bf16 value: four lanes x 8 channels per (query, head) like msda_fwd8_kernel (tuning key 4: 1 never, 2 always)
+    const int wide_mode = g_tuning[4].load();
+    if (wide_mode == 2 || (wide_mode == 0 && dtype == DEVIS_MSDA_BF16)) {
+        threads = g_tuning[0].load();
+        if (threads == 0) threads = num_query >= 1024 ? 128 : 64;
+        threads = threads < 32 ? 32 : threads > 256 ? 256 : (threads / 32) * 32;
+        const long long chunks = ((long long)num_query + threads / 4 - 1) / (threads / 4);
+        if (chunks * num_heads > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
+        grid = dim3((unsigned)(chunks * num_heads), (unsigned)num_frames);
+        smem = (size_t)(a.n_slots[0] + a.n_slots[1]) * sizeof(int4) + (size_t)(threads / 32) * Tap16::kBytesPerWarp;
+        if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd8_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else tmsda_fused_fwd8_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        return check_launch();
+    }
+    // two queries per lane group for fp32 at encoder sizes, like msda_fwdc_kernel (tuning key 1 overrides)
+    int qpg = g_tuning[1].load();
+    if (qpg != 1 && qpg != 2) qpg = (dtype == DEVIS_MSDA_F32 && num_query >= 2048) ? 2 : 1;
+    rc = fused_grid(a, 0, grid, threads, smem, qpg);
     if (rc) return rc;
-    if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-    else tmsda_fused_fwd_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    if (dtype == DEVIS_MSDA_BF16) {
+        if (qpg == 2) tmsda_fused_fwd_kernel<true, 2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else tmsda_fused_fwd_kernel<true, 1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if (qpg == 2) tmsda_fused_fwd_kernel<false, 2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else tmsda_fused_fwd_kernel<false, 1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    }
     return check_launch();
 }
 

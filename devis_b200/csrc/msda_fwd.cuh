@@ -364,6 +364,39 @@ __device__ __forceinline__ void ldg_bf16x8(const char *p, float (&v)[8])
     v[7] = __uint_as_float(r.w & 0xffff0000u);
 }
 
+// one exchange of 4 published records (4 lanes x 8 channels per row) -> 16 corner gathers and 128 FFMA per lane
+template <bool BF16>
+__device__ __forceinline__ void consume_tap16x4(const float *buf, int g, unsigned rowbytes, unsigned pitch,
+                                                const char *vbase, float (&acc)[8])
+{
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
+        const unsigned oTL = r.x & ~15u;
+        const unsigned dcol = (r.x & 1u) ? rowbytes : 0u, drow = (r.x & 2u) ? pitch : 0u;
+        const unsigned oTR = oTL + dcol, oBL = oTL + drow, oBR = oBL + dcol;
+        const float lw = __uint_as_float(r.w);
+        const float hwm = (r.x & 4u) ? 1.f - lw : 0.f, lwm = (r.x & 8u) ? lw : 0.f;
+        const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
+        const float c00 = whh * hwm, c01 = whh * lwm, c10 = wlh * hwm, c11 = wlh * lwm;
+        float v00[8], v01[8], v10[8], v11[8];
+        if (BF16) {
+            ldg_bf16x8(vbase + oTL, v00);
+            ldg_bf16x8(vbase + oTR, v01);
+            ldg_bf16x8(vbase + oBL, v10);
+            ldg_bf16x8(vbase + oBR, v11);
+        } else {
+            ldg_f8(vbase + oTL, v00);
+            ldg_f8(vbase + oTR, v01);
+            ldg_f8(vbase + oBL, v10);
+            ldg_f8(vbase + oBR, v11);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            acc[c] = fmaf(c11, v11[c], fmaf(c10, v10[c], fmaf(c01, v01[c], fmaf(c00, v00[c], acc[c]))));
+    }
+}
+
 template <bool BF16, int QPG, class SlotSrc>
 __global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a)
 {
@@ -429,32 +462,7 @@ __global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a
                 parity ^= 1;
                 *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = rec;
                 __syncwarp();
-#pragma unroll
-                for (int jj = 0; jj < LPG; ++jj) {
-                    const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
-                    const unsigned oTL = r.x & ~15u;
-                    const unsigned dcol = (r.x & 1u) ? rowbytes : 0u, drow = (r.x & 2u) ? pitch : 0u;
-                    const unsigned oTR = oTL + dcol, oBL = oTL + drow, oBR = oBL + dcol;
-                    const float lw = __uint_as_float(r.w);
-                    const float hwm = (r.x & 4u) ? 1.f - lw : 0.f, lwm = (r.x & 8u) ? lw : 0.f;
-                    const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
-                    const float c00 = whh * hwm, c01 = whh * lwm, c10 = wlh * hwm, c11 = wlh * lwm;
-                    float v00[8], v01[8], v10[8], v11[8];
-                    if (BF16) {
-                        ldg_bf16x8(vbase + oTL, v00);
-                        ldg_bf16x8(vbase + oTR, v01);
-                        ldg_bf16x8(vbase + oBL, v10);
-                        ldg_bf16x8(vbase + oBR, v11);
-                    } else {
-                        ldg_f8(vbase + oTL, v00);
-                        ldg_f8(vbase + oTR, v01);
-                        ldg_f8(vbase + oBL, v10);
-                        ldg_f8(vbase + oBR, v11);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        acc[i][c] = fmaf(c11, v11[c], fmaf(c10, v10[c], fmaf(c01, v01[c], fmaf(c00, v00[c], acc[i][c]))));
-                }
+                consume_tap16x4<BF16>(buf, g, rowbytes, pitch, vbase, acc[i]);
             }
         }
         slot_base += a.seg[sg].n_slots;

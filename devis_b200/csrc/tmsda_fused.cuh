@@ -41,7 +41,8 @@ struct FusedArgs {
     float *grad_logit[2];
 };
 
-// softmax statistics of one (query, head) row over both segments, computed by the 8 lanes of its group
+// softmax statistics of one (query, head) row over both segments, computed by the LPG lanes of its group
+template <int LPG = 8>
 __device__ __forceinline__ void row_softmax_stats(const FusedArgs &a, size_t row, int j, bool live, float &rmax,
                                                   float &rinv)
 {
@@ -49,37 +50,59 @@ __device__ __forceinline__ void row_softmax_stats(const FusedArgs &a, size_t row
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int K = a.n_slots[sg] * a.P[sg];
         const float *lg = a.logit[sg] + row * K;
-        for (int k = j; k < K; k += 8)
+        for (int k = j; k < K; k += LPG)
             if (live) mx = fmaxf(mx, __ldg(lg + k));
     }
 #pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, 8));
+    for (int o = LPG / 2; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, LPG));
     float sum = 0.f;
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int K = a.n_slots[sg] * a.P[sg];
         const float *lg = a.logit[sg] + row * K;
-        for (int k = j; k < K; k += 8)
+        for (int k = j; k < K; k += LPG)
             if (live) sum += expf(__ldg(lg + k) - mx);
     }
 #pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 8);
+    for (int o = LPG / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, LPG);
     rmax = live ? mx : 0.f;
     rinv = live ? 1.f / sum : 0.f;
 }
 
-// location and weight of tap k of segment sg for (query row): the fused prologue
-__device__ __forceinline__ void fused_tap_operands(const FusedArgs &a, int sg, size_t row, size_t qrow, int k, int K,
-                                                   const int4 sl, int level, float rmax, float rinv, float &x,
-                                                   float &y, float &w)
+// raw operands of one tap as the Linear layers wrote them; loaded one exchange AHEAD of their use (like
+// msda_fwdc_kernel's load_taps) so that their DRAM latency hides under the 32 corner gathers of the exchange before
+struct RawTap {
+    float2 off;   // sampling offset (pixels of the tap's level)
+    float2 rf;    // reference point the tap starts from
+    float lg;     // attention logit
+};
+
+__device__ __forceinline__ RawTap load_raw_tap(const FusedArgs &a, int sg, size_t row, size_t qrow, int k, bool live)
 {
-    const float2 off = __ldg(reinterpret_cast<const float2 *>(a.off[sg] + row * K * 2) + k);
-    const float2 rf = __ldg(reinterpret_cast<const float2 *>(a.ref + (qrow * a.src.L + (sg == 0 ? level : 0)) * 2));
-    x = __fadd_rn(rf.x, __fdiv_rn(off.x, (float)sl.y));
-    y = __fadd_rn(rf.y, __fdiv_rn(off.y, (float)sl.x));
-    w = expf(__ldg(a.logit[sg] + row * K + k) - rmax) * rinv;
+    RawTap r;
+    r.off = make_float2(0.f, 0.f);
+    r.rf = make_float2(0.f, 0.f);
+    r.lg = 0.f;
+    const int P = a.P[sg], K = a.n_slots[sg] * P;
+    if (live && k < K) {
+        const int level = (k / P) % a.src.L;
+        r.off = ld_stream_f2(reinterpret_cast<const float2 *>(a.off[sg] + row * K * 2) + k);
+        r.rf = __ldg(reinterpret_cast<const float2 *>(a.ref + (qrow * a.src.L + (sg == 0 ? level : 0)) * 2));
+        r.lg = __ldg(a.logit[sg] + row * K + k);      // in L1 since row_softmax_stats
+    }
+    return r;
 }
 
-template <bool BF16>
+// the fused prologue on prefetched operands:  loc = ref + off / (W, H)  with torch's own rounding (IEEE division, then
+// addition),  w = exp(logit - rowmax) / rowsum
+__device__ __forceinline__ void raw_to_operands(const RawTap &r, const int4 sl, float rmax, float rinv, float &x, float &y,
+                                                float &w)
+{
+    x = __fadd_rn(r.rf.x, __fdiv_rn(r.off.x, (float)sl.y));
+    y = __fadd_rn(r.rf.y, __fdiv_rn(r.off.y, (float)sl.x));
+    w = expf(r.lg - rmax) * rinv;
+}
+
+template <bool BF16, int QPG>
 __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
@@ -91,47 +114,142 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
     const int M = a.d.M, Lq = a.d.Lq;
     const int j = threadIdx.x % LPG, g = (threadIdx.x & 31) / LPG, grp = threadIdx.x / LPG, QC = blockDim.x / LPG;
     const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
-    const int qi = qchunk * QC + grp;
-    const bool qlive = qi < Lq;
-    const int q = qlive ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
-    const size_t qrow = (size_t)outer * Lq + q, row = qrow * M + m;
+    bool qlive[QPG];
+    size_t qrow[QPG], row[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        const int qi = (qchunk * QPG + i) * QC + grp;
+        qlive[i] = qi < Lq;
+        const int q = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
+        qrow[i] = (size_t)outer * Lq + q;
+        row[i] = qrow[i] * M + m;
+    }
 
     constexpr unsigned kQuadBytes = BF16 ? 8u : 16u;
     const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
     const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
     asm volatile("" : "+l"(vbase));
 
-    float rmax, rinv;
-    row_softmax_stats(a, row, j, qlive, rmax, rinv);
+    float rmax[QPG], rinv[QPG];
+    float4 acc[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        row_softmax_stats(a, row[i], j, qlive[i], rmax[i], rinv[i]);
+        acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    RawTap nxt[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, 0, row[i], qrow[i], j, qlive[i]);
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.P[sg], K = a.n_slots[sg] * P;             // P % 4 == 0 (checked by the launcher)
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
-            const bool live = k < K && qlive;
-            const int ls = k < K ? k / P : 0;                      // slot within the segment
+            const bool klive = k < K;
+            const int ls = klive ? k / P : 0;                      // slot within the segment
             const int4 sl = s_slot[slot_base + ls];
             const unsigned my_pitch = (unsigned)sl.y * rowbytes;
             const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);
             const unsigned pitch_hi = __shfl_sync(0xffffffffu, my_pitch, 4, 8);
+            RawTap cur[QPG];
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) cur[i] = nxt[i];
+            if (k0 + LPG < K) {
+#pragma unroll
+                for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, sg, row[i], qrow[i], k + LPG, qlive[i]);
+            } else if (sg + 1 < a.n_seg) {
+#pragma unroll
+                for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, sg + 1, row[i], qrow[i], j, qlive[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) {
+                const bool live = klive && qlive[i];
+                float x = 0.f, y = 0.f, w = 0.f;
+                if (live) raw_to_operands(cur[i], sl, rmax[i], rinv[i], x, y, w);
+                const TapGeom t = tap_geometry(x, y, sl, live);
+                float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
+                parity ^= 1;
+                *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
+                __syncwarp();
+                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i]);
+            }
+        }
+        slot_base += a.n_slots[sg];
+    }
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        if (!qlive[i]) continue;
+        if (BF16)
+            reinterpret_cast<uint2 *>(a.out)[row[i] * LPG + j] = pack_bf16x4(acc[i]);
+        else
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row[i] * LPG + j, acc[i]);
+    }
+}
+
+// Four lanes per (query, head), 8 channels per lane (msda_fwd8_kernel's shape): the forward of choice for bf16 value,
+// whose 64-byte rows cost 0.75 instead of 1.0 data-pipe cycles when 4 lanes fetch 16 bytes each.
+template <bool BF16>
+__global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a)
+{
+    constexpr int LPG = 4;
+    extern __shared__ int4 s_slot[];
+    const int outer = blockIdx.y, n_slots_total = a.n_slots[0] + (a.n_seg > 1 ? a.n_slots[1] : 0);
+    build_slots(s_slot, a.src, a.d, outer, n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16::kWordsPerWarpBuf);
+
+    const int M = a.d.M, Lq = a.d.Lq;
+    const int j = threadIdx.x & 3, g = (threadIdx.x & 31) >> 2, grp = threadIdx.x >> 2, QC = blockDim.x >> 2;
+    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+    const int qi = qchunk * QC + grp;
+    const bool qlive = qi < Lq;
+    const int q = qlive ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
+    const size_t qrow = (size_t)outer * Lq + q, row = qrow * M + m;
+
+    constexpr unsigned kLaneBytes = BF16 ? 16u : 32u;      // 8 channels
+    const unsigned rowbytes = (unsigned)(M * LPG) * kLaneBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kLaneBytes;
+    asm volatile("" : "+l"(vbase));
+
+    float rmax, rinv;
+    row_softmax_stats<LPG>(a, row, j, qlive, rmax, rinv);
+
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+
+    RawTap nxt = load_raw_tap(a, 0, row, qrow, j, qlive);
+    int slot_base = 0, parity = 0;
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const int P = a.P[sg], K = a.n_slots[sg] * P;             // P % 4 == 0: one slot per exchange, k < K always
+        for (int k0 = 0; k0 < K; k0 += LPG) {
+            const int k = k0 + j;
+            const int4 sl = s_slot[slot_base + k0 / P];
+            const unsigned pitch = (unsigned)sl.y * rowbytes;
+            const RawTap cur = nxt;
+            if (k0 + LPG < K) nxt = load_raw_tap(a, sg, row, qrow, k + LPG, qlive);
+            else if (sg + 1 < a.n_seg) nxt = load_raw_tap(a, sg + 1, row, qrow, j, qlive);
             float x = 0.f, y = 0.f, w = 0.f;
-            if (live) fused_tap_operands(a, sg, row, qrow, k, K, sl, ls % a.src.L, rmax, rinv, x, y, w);
-            const TapGeom t = tap_geometry(x, y, sl, live);
-            float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
+            if (qlive) raw_to_operands(cur, sl, rmax, rinv, x, y, w);
+            const TapGeom t = tap_geometry(x, y, sl, qlive);
+            float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
             parity ^= 1;
-            *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
+            *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16(t, w, rowbytes);
             __syncwarp();
-            consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc);
+            consume_tap16x4<BF16>(buf, g, rowbytes, pitch, vbase, acc);
         }
         slot_base += a.n_slots[sg];
     }
     if (qlive) {
-        if (BF16)
-            reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc);
-        else
-            reinterpret_cast<float4 *>(a.out)[row * LPG + j] = acc;
+        if (BF16) {
+            const uint2 lo = pack_bf16x4(make_float4(acc[0], acc[1], acc[2], acc[3]));
+            const uint2 hi = pack_bf16x4(make_float4(acc[4], acc[5], acc[6], acc[7]));
+            reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+            float4 *o = reinterpret_cast<float4 *>(a.out) + (row * LPG + j) * 2;
+            o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
 }
 
@@ -172,6 +290,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
 
     float dotp = 0.f;   // this lane's share of sum_k w_k * d(out.grad_out)/d(w_k)
     int slot_base = 0, parity = 0;
+    RawTap nxt = load_raw_tap(a, 0, row, qrow, j, qlive);
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.P[sg], K = a.n_slots[sg] * P;
         float *goff = a.grad_off[sg] + row * K * 2;
@@ -181,8 +300,11 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
             const bool live = k < K && qlive;
             const int ls = live ? k / P : 0;
             const int4 sl = s_slot[slot_base + ls];
+            const RawTap cur = nxt;
+            if (k0 + LPG < K) nxt = load_raw_tap(a, sg, row, qrow, k + LPG, qlive);
+            else if (sg + 1 < a.n_seg) nxt = load_raw_tap(a, sg + 1, row, qrow, j, qlive);
             float x = 0.f, y = 0.f, w = 0.f;
-            if (live) fused_tap_operands(a, sg, row, qrow, k, K, sl, ls % a.src.L, rmax, rinv, x, y, w);
+            if (live) raw_to_operands(cur, sl, rmax, rinv, x, y, w);
             const TapGeom t = tap_geometry(x, y, sl, live);
             float *buf = xbuf + parity * X::kWordsPerWarpBuf;
             parity ^= 1;
@@ -231,7 +353,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
                 const float gy = hw * (b_in * A[2] - t_in * A[0]) + lw * (b_in * A[3] - t_in * A[1]);
                 // d/d(loc) as in msda_bwd.cuh, then the chain rule of loc = ref + off / (W, H)
                 const float glx = hit ? (float)sl.y * gx * w : 0.f, gly = hit ? (float)sl.x * gy * w : 0.f;
-                reinterpret_cast<float2 *>(goff)[k] = make_float2(__fdiv_rn(glx, (float)sl.y), __fdiv_rn(gly, (float)sl.x));
+                st_stream_f2(reinterpret_cast<float2 *>(goff) + k, make_float2(__fdiv_rn(glx, (float)sl.y), __fdiv_rn(gly, (float)sl.x)));
                 glog[k] = val;            // parked; finished below once the row's  sum_k w_k val_k  is known
                 dotp = fmaf(w, val, dotp);
             }
