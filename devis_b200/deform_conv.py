@@ -51,6 +51,24 @@ _COLS_CHUNK_BYTES = 256 << 20          # recomputed columns per weight-gradient 
 _packed_cache = {}
 
 
+def _wgrad(g2, cols):
+    """grad_out^T x columns: (rows, Cout)^T x (rows, K*C) -> (Cout, K*C).  The reduction runs over rows = N*Ho*Wo
+    (10^5 .. 10^6) while the product is tiny for the narrow mask-head layers; as ONE GEMM cuBLAS picks sgemm_largek
+    and runs at 4 TFLOP/s (512 us for 16 x 216000 x 288, `benchmarks/dcn_profile.py`).  Independent row slabs as a
+    batched GEMM + a sum of the partial products read the columns at memory speed instead."""
+    rows, cout = g2.shape
+    kc = cols.shape[1]
+    slab = 2048
+    if cout > 1 and cout * kc <= (1 << 17) and rows >= 8 * slab:
+        s = rows // slab
+        main = s * slab
+        out = torch.bmm(g2[:main].view(s, slab, cout).transpose(1, 2), cols[:main].view(s, slab, kc)).sum(0)
+        if main < rows:
+            out.addmm_(g2[main:].t(), cols[main:rows])
+        return out
+    return g2.t() @ cols[:rows]
+
+
 def set_fused(enabled):
     """enable / disable the fused gather+contraction kernels (default on); returns the previous setting"""
     global _FUSED
@@ -158,7 +176,7 @@ class FusedDeformConv2dFunction(Function):
                     _lib.check(lib.devis_dcn_im2col(_ptr(x[n0:n1]), _ptr(offset[n0:n1]),
                                                     _ptr(mask[n0:n1]) if mask is not None else None, _ptr(cols),
                                                     n1 - n0, *ctx.dims[1:], _DTYPES[x.dtype], stream))
-                    gw2.addmm_(g2[n0 * ho * wo:n1 * ho * wo].t(), cols[:rows])
+                    gw2 += _wgrad(g2[n0 * ho * wo:n1 * ho * wo], cols[:rows])
                 grad_w = gw2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
         if need_b and ctx.has_bias:
             grad_b = g.sum((0, 1, 2))
@@ -202,7 +220,7 @@ class DeformConv2dFunction(Function):
         need_in, need_off, need_w, need_b, need_m = ctx.needs_input_grad[:5]
         grad_w = grad_b = grad_in = grad_off = grad_m = None
         if need_w:
-            grad_w = (g2.t() @ cols).view(cout, kh, kw, c).permute(0, 3, 1, 2)
+            grad_w = _wgrad(g2, cols).view(cout, kh, kw, c).permute(0, 3, 1, 2)
         if need_b and ctx.has_bias:
             grad_b = g2.sum(0)
         if need_in or need_off or (need_m and mask is not None):
