@@ -351,9 +351,9 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
                 const float val = hit ? hh * (hw * A[0] + lw * A[1]) + lh * (hw * A[2] + lw * A[3]) : 0.f;
                 const float gx = hh * (r_in * A[1] - l_in * A[0]) + lh * (r_in * A[3] - l_in * A[2]);
                 const float gy = hw * (b_in * A[2] - t_in * A[0]) + lw * (b_in * A[3] - t_in * A[1]);
-                // d/d(loc) as in msda_bwd.cuh, then the chain rule of loc = ref + off / (W, H)
-                const float glx = hit ? (float)sl.y * gx * w : 0.f, gly = hit ? (float)sl.x * gy * w : 0.f;
-                st_stream_f2(reinterpret_cast<float2 *>(goff) + k, make_float2(__fdiv_rn(glx, (float)sl.y), __fdiv_rn(gly, (float)sl.x)));
+                // d/d(loc) = (W gx w, H gy w) as in msda_bwd.cuh, then the chain rule of loc = ref + off / (W, H): the two
+                // factors cancel (the reference's multiply-then-divide sequence differs from this by <= 1 ulp)
+                st_stream_f2(reinterpret_cast<float2 *>(goff) + k, hit ? make_float2(gx * w, gy * w) : make_float2(0.f, 0.f));
                 glog[k] = val;            // parked; finished below once the row's  sum_k w_k val_k  is known
                 dotp = fmaf(w, val, dotp);
             }
