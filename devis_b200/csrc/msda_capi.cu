@@ -782,6 +782,15 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
     size_t smem;
     rc = fused_grid(a, 2, grid, threads, smem);
     if (rc) return rc;
+    {   // (weight, d/d weight) of every tap parked in shared memory until the row's softmax-backward sum is known
+        int iters = 0;
+        for (int sg = 0; sg < a.n_seg; ++sg) iters += (a.n_slots[sg] * a.P[sg] + 7) / 8;
+        const size_t park = (size_t)iters * threads * sizeof(float2);
+        if (smem + park <= 48 * 1024) {
+            a.park_iters = iters;
+            smem += park;
+        }
+    }
     if (half_acc) tmsda_fused_bwd_kernel<true, true><<<grid, threads, smem, st>>>(a);
     else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
     else tmsda_fused_bwd_kernel<false><<<grid, threads, smem, st>>>(a);

@@ -39,6 +39,7 @@ struct FusedArgs {
     void *grad_value;          // fp32 (bf16 under HALF_ACC)
     float *grad_off[2];
     float *grad_logit[2];
+    int park_iters;            // > 0: shared memory holds (weight, d/d weight) of that many exchanges per thread
 };
 
 // softmax statistics of one (query, head) row over both segments, computed by the LPG lanes of its group
@@ -263,6 +264,13 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
     const int outer = blockIdx.y, n_slots_total = a.n_slots[0] + (a.n_seg > 1 ? a.n_slots[1] : 0);
     build_slots(s_slot, a.src, a.d, outer, n_slots_total);
     float *xbuf = reinterpret_cast<float *>(s_slot + n_slots_total) + (threadIdx.x >> 5) * (2 * X::kWordsPerWarpBuf);
+    // softmax backward needs sum_k w_k val_k of the whole row before any d/d(logit) can be written: each thread parks the
+    // (w, val) of the taps it prepared -- in shared memory when the row is short enough ([exchange][thread], conflict-free,
+    // read back by the same thread: no barrier), else in grad_logit itself (re-read through L2: 13 % of the kernel's
+    // stall samples sat in that epilogue, profiles/r1j_fused_bwd_stalls.json)
+    float2 *s_park = reinterpret_cast<float2 *>(reinterpret_cast<float *>(s_slot + n_slots_total) +
+                                                (blockDim.x >> 5) * (2 * X::kWordsPerWarpBuf)) + threadIdx.x;
+    const bool park = a.park_iters > 0;
 
     const int M = a.d.M, Lq = a.d.Lq;
     const int j = threadIdx.x % LPG, g = (threadIdx.x & 31) / LPG, grp = threadIdx.x / LPG, QC = blockDim.x / LPG;
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
     row_softmax_stats(a, row, j, qlive, rmax, rinv);
 
     float dotp = 0.f;   // this lane's share of sum_k w_k * d(out.grad_out)/d(w_k)
-    int slot_base = 0, parity = 0;
+    int slot_base = 0, parity = 0, it = 0;
     RawTap nxt = load_raw_tap(a, 0, row, qrow, j, qlive);
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.P[sg], K = a.n_slots[sg] * P;
@@ -354,9 +362,11 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
                 // d/d(loc) = (W gx w, H gy w) as in msda_bwd.cuh, then the chain rule of loc = ref + off / (W, H): the two
                 // factors cancel (the reference's multiply-then-divide sequence differs from this by <= 1 ulp)
                 st_stream_f2(reinterpret_cast<float2 *>(goff) + k, hit ? make_float2(gx * w, gy * w) : make_float2(0.f, 0.f));
-                glog[k] = val;            // parked; finished below once the row's  sum_k w_k val_k  is known
+                if (park) s_park[it * blockDim.x] = make_float2(w, val);
+                else glog[k] = val;       // parked; finished below once the row's  sum_k w_k val_k  is known
                 dotp = fmaf(w, val, dotp);
             }
+            ++it;
         }
         slot_base += a.n_slots[sg];
     }
@@ -364,13 +374,22 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
 #pragma unroll
     for (int o = 4; o >= 1; o >>= 1) dotp += __shfl_xor_sync(0xffffffffu, dotp, o, 8);
     if (qlive) {
+        it = 0;
         for (int sg = 0; sg < a.n_seg; ++sg) {
             const int K = a.n_slots[sg] * a.P[sg];
             float *glog = a.grad_logit[sg] + row * K;
             const float *lg = a.logit[sg] + row * K;
-            for (int k = j; k < K; k += 8) {
-                const float w = expf(__ldg(lg + k) - rmax) * rinv;
-                glog[k] = w * (glog[k] - dotp);
+            if (park) {
+                for (int k = j; k < K; k += 8, ++it) {
+                    const float2 wv = s_park[it * blockDim.x];
+                    st_stream_f(glog + k, wv.x * (wv.y - dotp));
+                }
+                it += (j >= K % 8 && K % 8 != 0) ? 1 : 0;     // exchanges are counted per group, not per lane
+            } else {
+                for (int k = j; k < K; k += 8) {
+                    const float w = expf(__ldg(lg + k) - rmax) * rinv;
+                    glog[k] = w * (glog[k] - dotp);
+                }
             }
         }
     }
