@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--dist", default="local")
     ap.add_argument("--out", default="")
     ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--only-batched", action="store_true", help="only the batched MSDeformAttn shape (section iv)")
     a = ap.parse_args()
     ref = ref_cuda_build.load()
     assert ref is not None, "oracle/_ref not built"
@@ -60,6 +61,31 @@ def main():
         tmp = (clip["value"][clip["frame_table"][t]].flatten(0, 1)[None].contiguous(), tshapes, lsi_of(tshapes),
                clip["loc_temporal"][t][None].contiguous(), clip["aw_temporal"][t][None].contiguous())
         return cur, tmp
+
+    # (iv) the plain batched op of MSDeformAttn (ms_deform_attn.py:84-132): COCO pre-training encoder
+    # shape, 800 x 1333 input -> levels /8 .. /64, batch 2, one query per pixel, 4 levels x 4 points
+    def batched():
+        coco = ((100, 167), (50, 84), (25, 42), (13, 21))
+        bclip = synthetic.make_clip(n_frames=2, shapes=coco, dist=a.dist, seed=4, device="cuda", t_window=1)
+        bshapes = torch.tensor(coco, device="cuda")
+        args = (bclip["value"], bshapes, lsi_of(bshapes), bclip["loc_curr"], bclip["aw_curr"])
+        gout = bclip["grad_out"]
+        row = {"batch": 2, "S": int(bclip["value"].shape[1]), "Lq": int(bclip["loc_curr"].shape[1])}
+        outs = {}
+        for impl, mod in (("ref", ref), ("ours", ours)):
+            row[impl + "_fwd_us"] = med_us(lambda: mod.ms_deform_attn_forward(*args, 64), a.iters)
+            row[impl + "_bwd_us"] = med_us(lambda: mod.ms_deform_attn_backward(*args, gout, 64), a.iters)
+            outs[impl] = mod.ms_deform_attn_forward(*args, 64)
+        row["max_abs_diff"] = float((outs["ref"] - outs["ours"]).abs().max())
+        print("batched MSDeformAttn", row, flush=True)
+        return row
+
+    if a.only_batched:
+        res["batched_msdeformattn_coco_encoder"] = batched()
+        if a.out:
+            with open(a.out, "w") as fh:
+                json.dump(res, fh, indent=1)
+        return
 
     # (i) per call
     per_call = {}
@@ -171,6 +197,7 @@ def main():
                          "ours_whole_clip_fwd_us": med_us(drc.fwd, a.iters), "ours_whole_clip_bwd_us": med_us(drc.bwd, a.iters)}
         print("decoder", lq, dec[f"q{lq}"], flush=True)
     res["decoder_layer_clip"] = dec
+    res["batched_msdeformattn_coco_encoder"] = batched()
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(res, fh, indent=1)
