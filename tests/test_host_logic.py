@@ -203,3 +203,39 @@ def test_decoder_mirror_scales_reference_points_like_the_reference():
         assert np.array_equal(seen["tshapes"].numpy(), g["tshapes"]) and np.array_equal(seen["tlsi"].numpy(), g["tlsi"])
         assert seen["offsets"] == g["temporal_offsets"].tolist()
         assert hs.shape[0] == 1 and torch.equal(refs[0], ref)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys,
+    same metric / unit / workload as our arm, a cpu_baseline describing the run and zero-copy e2e."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "temporal_msda_fwd_bwd_layer_clips_per_sec"
+    assert line["unit"] == "layer-clips/s" and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert abs(line["value"] - 1e3 / line["ms_per_step"]) < 1e-6 * line["value"]
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_weight_gradient_split_rows_equals_one_gemm():
+    """deform_conv._wgrad: the batched split-row product (taken for narrow layers with 10^5+ rows) and the single GEMM
+    agree; odd row counts exercise the remainder slab."""
+    from devis_b200 import deform_conv
+    g = torch.Generator().manual_seed(0)
+    for rows, cout, kc in ((8 * 2048 + 77, 16, 288), (8 * 2048, 4, 36), (1000, 16, 288), (8 * 2048 + 5, 1, 144)):
+        g2 = torch.randn(rows, cout, generator=g, dtype=torch.float64)
+        cols = torch.randn(rows + 3, kc, generator=g, dtype=torch.float64)
+        got = deform_conv._wgrad(g2, cols[:rows])
+        want = g2.t() @ cols[:rows]
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-12, atol=1e-10)
