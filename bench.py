@@ -386,7 +386,8 @@ def run_ours(args, rank, world, local_rank):
                          "fwd_bwd": {"achieved": (bytes_f + bytes_b) / (us_fwd + us_bwd) / 1e3,
                                      "frac": (bytes_f + bytes_b) / (us_fwd + us_bwd) / 1e3 / peak},
                          "note": "contract roofline (HBM). Binding resources measured with ncu + microbenchmarks: forward = SM "
-                                 "L1/shared data pipe (~77 % of peak), backward = SM reduction egress (~25 B/clk/SM, 100 %); "
+                                 "L1/shared data pipe (~77 % of peak), backward = SM reduction egress (~25 B/clk/SM, 79 % busy) together with "
+                                 "the data pipe (71 %); "
                                  "DESIGN.md 3.6, profiles/README.md"},
             "e2e": {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "runs_ms_per_step": [round(x, 3) for x in e2e_runs], "steps_per_run": e2e_steps,
