@@ -300,6 +300,37 @@ def run_ours(args, rank, world, local_rank):
             extra["error"] = str(exc)[:200]
     fwd_kernel = "msda_fwdc_kernel" if dtype == torch.float32 else "msda_fwd8_kernel"   # what the launcher picks at D = 32
 
+    # ---- the on-chip resources that actually bind: every tap gathers 4 value rows through the SM's
+    # L1 data pipe (128 B/clk/SM), every live corner leaves the SM as one row reduction (5.16 cycles per 128-B row,
+    # benchmarks/micro/tma_reduce.cu).  Counted from this step's own taps, timed live.
+    def live_corners():
+        n = 0
+        for loc, reps in ((clip["loc_curr"], 1), (clip["loc_temporal"], T_FRAMES - 1)):
+            size = torch.tensor([[w, h] for h, w in clip["shapes"]], device=dev, dtype=torch.float32).repeat(reps, 1)
+            pix = loc.detach().float() * size[None, None, None, :, None, :] - 0.5
+            x, y = pix[..., 0], pix[..., 1]
+            wl, hl = size[:, 0][None, None, None, :, None], size[:, 1][None, None, None, :, None]
+            inr = (x > -1) & (y > -1) & (x < wl) & (y < hl)
+            x0, y0 = torch.floor(x), torch.floor(y)
+            lft, rgt, top, bot = x0 >= 0, x0 + 1 <= wl - 1, y0 >= 0, y0 + 1 <= hl - 1
+            n += int(((inr & top & lft).sum() + (inr & top & rgt).sum() + (inr & bot & lft).sum() + (inr & bot & rgt).sum()).item())
+        return n
+
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+    row_bytes = CH * elem
+    gather_bytes = T_FRAMES * S_ROWS * HEADS * K_TAPS * 4 * row_bytes
+    l1_peak = sm_count * 128 * sm_hz                      # bytes per second through the L1/shared data pipes
+    red_rows = live_corners()
+    on_chip = {
+        "fwd_l1_gather": {"bytes": gather_bytes, "achieved_TBps": gather_bytes / us_fwd / 1e6, "peak_TBps": l1_peak / 1e12,
+                          "frac": gather_bytes / (us_fwd * 1e-6) / l1_peak},
+        "bwd_reduction_egress": {"row_reductions": red_rows, "cycles_per_row": 5.16,
+                                 "busy_frac": red_rows / sm_count * 5.16 / (us_bwd * 1e-6 * sm_hz)},
+        "note": "gathered value rows through the SMs' L1 data pipes (128 B/clk/SM at the sampled SM clock) and grad_value row "
+                "reductions leaving the SMs (5.16 cycles per 128-B row measured); these, not HBM, bound the kernels",
+    }
+
     # ---- e2e: public autograd API driven from pinned HOST buffers.  Every step copies its six operands host->device
     # and its six results device->host; copies of neighbouring steps overlap the kernels (three streams, two
     # buffer sets), as any host-fed pipeline would run it.  Timed with events on the compute stream + a final sync.
@@ -388,7 +419,8 @@ def run_ours(args, rank, world, local_rank):
                          "note": "contract roofline (HBM). Binding resources measured with ncu + microbenchmarks: forward = SM "
                                  "L1/shared data pipe (~77 % of peak), backward = SM reduction egress (~25 B/clk/SM, 79 % busy) together with "
                                  "the data pipe (71 %); "
-                                 "DESIGN.md 3.6, profiles/README.md"},
+                                 "DESIGN.md 3.6, profiles/README.md",
+                         "on_chip": on_chip},
             "e2e": {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "runs_ms_per_step": [round(x, 3) for x in e2e_runs], "steps_per_run": e2e_steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
