@@ -41,6 +41,8 @@ SIGNATURES = {
     "devis_dcn_pack_weight": (_i, [_vp] * 2 + [_i] * 4 + [_vp]),
     "devis_dcn_fused_forward": (_i, [_vp] * 6 + [_i] * 15 + [_vp]),
     "devis_dcn_fused_backward": (_i, [_vp] * 8 + [_i] * 15 + [_vp]),
+    "devis_dcn_wgrad_supported": (_i, [_i] * 5),
+    "devis_dcn_weight_grad": (_i, [_vp] * 5 + [_i] * 15 + [_vp]),
 }
 
 _lib = None

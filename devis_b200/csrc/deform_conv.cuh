@@ -675,4 +675,114 @@ __global__ void __launch_bounds__(256, CT == 16 ? 3 : 2)
     }
 }
 
+// =====================================================================================================================
+// Weight gradient without the column matrix (narrow layers: C = 4 * G channels, COUT <= 16):
+//     grad_w[co][k][c] = sum over output pixels of  mask * bilinear(input[.., c])  *  grad_out[pixel][co]
+// torchvision (and the im2col route here) writes the columns -- K x the input, 995 MB for 60 instances at 90 x 160 x 32 --
+// and multiplies them with grad_out^T in a GEMM whose reduction dimension is the pixel count.  Here a lane group of G
+// lanes owns kernel position k = blockIdx.y and a strided run of output pixels; a lane gathers and interpolates its four
+// channels of a pixel exactly like dcn_im2col_kernel, multiplies them with the pixel's COUT output gradients (one
+// broadcast load per four) and keeps the 4 x COUT partial sums in registers for the whole run.  The groups of a block are
+// then added up (shuffles inside a warp, shared memory across warps) and ONE atomic per (k, c, co) and block goes to
+// grad_w.  Nothing of column size exists at any point.
+// =====================================================================================================================
+template <int COUT, int G>
+__global__ void __launch_bounds__(256) dcn_wgrad_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+                                                        const float *__restrict__ mask, const float *__restrict__ grad_out,
+                                                        float *__restrict__ grad_w, DcnDims d, int n_base, int run)
+{
+    constexpr int GPB = 256 / G;                    // lane groups per block
+    constexpr int C = 4 * G;
+    __shared__ float red_s[8][C * COUT];
+    const int j = threadIdx.x % G, grp = threadIdx.x / G, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = n_base + (int)blockIdx.z, k = (int)blockIdx.y;
+    const int plane = d.Ho * d.Wo;
+    const float4 *img = reinterpret_cast<const float4 *>(input + (long long)n * d.H * d.W * C);
+    float acc[4][COUT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[i][co] = 0.f;
+
+    // pixel of iteration r: consecutive groups take consecutive pixels (coalesced offsets, shared gather neighbourhoods);
+    // the sampling point of iteration r + 1 is loaded while iteration r gathers (one dependent latency less per pixel)
+    const int K_ = d.kh * d.kw;
+    const float *off_h = offset + ((long long)n * 2 * K_ + 2 * k) * plane, *off_w = off_h + plane;
+    const float *msk = mask ? mask + ((long long)n * K_ + k) * plane : nullptr;
+    const int ky = k / d.kw, kx = k - ky * d.kw;
+    const int pp0 = (int)blockIdx.x * run * GPB + grp;
+    float n_oh = 0.f, n_ow = 0.f, n_m = 1.f;
+    if (pp0 < plane) {
+        n_oh = __ldg(off_h + pp0);
+        n_ow = __ldg(off_w + pp0);
+        if (msk) n_m = __ldg(msk + pp0);
+    }
+    for (int r = 0; r < run; ++r) {
+        const int pp = pp0 + r * GPB;
+        const float c_oh = n_oh, c_ow = n_ow, m = n_m;
+        if (r + 1 < run && pp + GPB < plane) {
+            n_oh = __ldg(off_h + pp + GPB);
+            n_ow = __ldg(off_w + pp + GPB);
+            if (msk) n_m = __ldg(msk + pp + GPB);
+        }
+        if (pp < plane) {
+            const DcnTapId id = dcn_tap_id(pp, n, k, d);
+            const float h = (float)(id.ho * d.sh - d.ph + ky * d.dh) + c_oh;
+            const float w = (float)(id.wo * d.sw - d.pw + kx * d.dw) + c_ow;
+            const DcnTap<float> t = dcn_tap(h, w, d.H, d.W);
+            const float f0 = m * t.w[0], f1 = m * t.w[1], f2 = m * t.w[2], f3 = m * t.w[3];
+            const float4 a = __ldg(img + (long long)t.row[0] * G + j), b = __ldg(img + (long long)t.row[1] * G + j);
+            const float4 e = __ldg(img + (long long)t.row[2] * G + j), f = __ldg(img + (long long)t.row[3] * G + j);
+            float v[4];
+            v[0] = f0 * a.x + f1 * b.x + f2 * e.x + f3 * f.x;
+            v[1] = f0 * a.y + f1 * b.y + f2 * e.y + f3 * f.y;
+            v[2] = f0 * a.z + f1 * b.z + f2 * e.z + f3 * f.z;
+            v[3] = f0 * a.w + f1 * b.w + f2 * e.w + f3 * f.w;
+            const float *g = grad_out + id.pixel * COUT;
+            if (COUT % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < COUT / 4; ++q) {
+                    const float4 gq = __ldg(reinterpret_cast<const float4 *>(g) + q);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][4 * q + 0] = fmaf(v[i], gq.x, acc[i][4 * q + 0]);
+                        acc[i][4 * q + 1] = fmaf(v[i], gq.y, acc[i][4 * q + 1]);
+                        acc[i][4 * q + 2] = fmaf(v[i], gq.z, acc[i][4 * q + 2]);
+                        acc[i][4 * q + 3] = fmaf(v[i], gq.w, acc[i][4 * q + 3]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float gc = __ldg(g + co);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i][co] = fmaf(v[i], gc, acc[i][co]);
+                }
+            }
+        }
+    }
+    // groups of a warp (same lane index j, 32 / G of them) by xor shuffles; every lane ends up with the warp's sum
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[i][co] += __shfl_xor_sync(0xffffffffu, acc[i][co], o);
+    if (lane < G) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) red_s[warp][co * C + 4 * j + i] = acc[i][co];
+    }
+    __syncthreads();
+    const int K = d.kh * d.kw;
+    for (int idx = threadIdx.x; idx < C * COUT; idx += 256) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) sum += red_s[wv][idx];
+        const int co = idx / C, c = idx - co * C;
+        atomicAdd(grad_w + ((long long)co * K + k) * C + c, sum);
+    }
+}
+
 }  // namespace devis

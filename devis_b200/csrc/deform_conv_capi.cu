@@ -345,4 +345,61 @@ int devis_dcn_fused_backward(const void *input, const void *offset, const void *
     return DEVIS_MSDA_OK;
 }
 
+/* devis_dcn_wgrad: 1 if devis_dcn_weight_grad serves the layer (float32, C in {16, 32}, out_channels in {1, 2, 4, 8, 16}) */
+int devis_dcn_wgrad_supported(int channels, int out_channels, int kernel_h, int kernel_w, int dtype)
+{
+    if (dtype != DEVIS_MSDA_F32 || kernel_h <= 0 || kernel_w <= 0 || kernel_h * kernel_w > 65535) return 0;
+    if (channels != 16 && channels != 32) return 0;
+    return out_channels == 1 || out_channels == 2 || out_channels == 4 || out_channels == 8 || out_channels == 16;
+}
+
+int devis_dcn_weight_grad(const void *input, const void *offset, const void *mask, const void *grad_out, void *grad_weight,
+                          int batch, int height, int width, int channels, int out_h, int out_w, int kernel_h,
+                          int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                          int out_channels, void *stream)
+{
+    const DcnDims d{batch, height, width, channels, out_h, out_w, kernel_h, kernel_w,
+                    stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
+    const int rc = check_dims(d, DEVIS_MSDA_F32);
+    if (rc) return rc;
+    if (!devis_dcn_wgrad_supported(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32)) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    if (!grad_weight) return DEVIS_MSDA_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t wbytes = (size_t)out_channels * kernel_h * kernel_w * channels * 4;
+    const cudaError_t e = cudaMemsetAsync(grad_weight, 0, wbytes, st);
+    if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+    const long long plane = (long long)out_h * out_w;
+    if ((long long)batch * plane == 0) return DEVIS_MSDA_OK;
+    if (!input || !offset || !grad_out) return DEVIS_MSDA_ERR_NULL_POINTER;
+    if (plane >= (1LL << 30) || (long long)height * width * channels >= (1LL << 31)) return DEVIS_MSDA_ERR_TOO_LARGE;
+    const int G = channels / 4, gpb = 256 / G;
+    // pixels per lane group: long runs amortise the block reduction, but keep >= ~4 blocks per SM in flight
+    int run = 64;
+    while (run > 8 && ((plane + (long long)gpb * run - 1) / ((long long)gpb * run)) * kernel_h * kernel_w * batch < 148 * 8) run /= 2;
+    const unsigned gx = (unsigned)((plane + (long long)gpb * run - 1) / ((long long)gpb * run));
+    const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask, *go = (const float *)grad_out;
+    float *gw = (float *)grad_weight;
+    for (int n0 = 0; n0 < batch; n0 += kMaxGridZ) {
+        const dim3 grid(gx, (unsigned)(kernel_h * kernel_w), (unsigned)(batch - n0 < kMaxGridZ ? batch - n0 : kMaxGridZ));
+#define DCN_WGRAD(CO, GG) dcn_wgrad_kernel<CO, GG><<<grid, 256, 0, st>>>(in, of, mk, go, gw, d, n0, run)
+#define DCN_WGRAD_G(CO)                      \
+    do {                                     \
+        if (G == 8) DCN_WGRAD(CO, 8);        \
+        else DCN_WGRAD(CO, 4);               \
+    } while (0)
+        switch (out_channels) {
+        case 1: DCN_WGRAD_G(1); break;
+        case 2: DCN_WGRAD_G(2); break;
+        case 4: DCN_WGRAD_G(4); break;
+        case 8: DCN_WGRAD_G(8); break;
+        default: DCN_WGRAD_G(16); break;
+        }
+#undef DCN_WGRAD_G
+#undef DCN_WGRAD
+        const int rc2 = devis_capi_check_launch();
+        if (rc2) return rc2;
+    }
+    return DEVIS_MSDA_OK;
+}
+
 }  // extern "C"

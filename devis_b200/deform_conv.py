@@ -164,7 +164,13 @@ class FusedDeformConv2dFunction(Function):
                                                         _ptr(grad_m[n0:n1]) if mask is not None else None, n1 - n0,
                                                         *ctx.dims[1:], _DTYPES[x.dtype], stream))
                 grad_in = gx.permute(0, 3, 1, 2) if need_in else None
-            if need_w:
+            if need_w and x.dtype == torch.float32 and lib.devis_dcn_wgrad_supported(c, cout, kh, kw, _DTYPES[x.dtype]):
+                # narrow layers: gather + contraction with grad_out in one kernel, no column matrix (dcn_wgrad_kernel)
+                gw3 = torch.empty((cout, k, c), dtype=x.dtype, device=x.device)
+                _lib.check(lib.devis_dcn_weight_grad(_ptr(x), _ptr(offset), _ptr(mask), _ptr(g), _ptr(gw3), *ctx.dims,
+                                                     cout, stream))
+                grad_w = gw3.view(cout, kh, kw, c).permute(0, 3, 1, 2)
+            elif need_w:
                 # cols^T x grad_out from columns recomputed a bounded chunk of the batch at a time
                 per = max(1, min(n, _COLS_CHUNK_BYTES // max(1, ho * wo * k * c * 4)))
                 cols = torch.empty((per * ho * wo, k * c), dtype=x.dtype, device=x.device)

@@ -74,6 +74,18 @@ int devis_dcn_fused_backward(const void *input_nhwc, const void *offset, const v
                              int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                              int out_channels, void *stream);
 
+/* devis_dcn_weight_grad: the weight gradient of a narrow layer without a column matrix,
+ *   grad_weight[co][k][c] = sum over (n, ho, wo) of mask * bilinear(input[n, .., c]) * grad_out_nhwc[n, ho, wo, co]
+ * i.e. (out_channels, kernel_h * kernel_w, channels) row-major, zero-filled here; permute to (Cout, C, kh, kw) on the
+ * caller's side.  Replaces torchvision's deformable_im2col + at::addmm pair of the backward
+ * (torchvision/csrc/ops/cuda/deform_conv2d_kernel.cu, backward_gradient_parameters) for float32 layers with
+ * channels in {16, 32} and out_channels in {1, 2, 4, 8, 16}: devis_dcn_wgrad_supported says so (1 / 0). */
+int devis_dcn_wgrad_supported(int channels, int out_channels, int kernel_h, int kernel_w, int dtype);
+int devis_dcn_weight_grad(const void *input_nhwc, const void *offset, const void *mask, const void *grad_out_nhwc,
+                          void *grad_weight, int batch, int height, int width, int channels, int out_h, int out_w,
+                          int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
+                          int dil_w, int out_channels, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
