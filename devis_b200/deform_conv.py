@@ -164,11 +164,11 @@ class FusedDeformConv2dFunction(Function):
                                                         _ptr(grad_m[n0:n1]) if mask is not None else None, n1 - n0,
                                                         *ctx.dims[1:], _DTYPES[x.dtype], stream))
                 grad_in = gx.permute(0, 3, 1, 2) if need_in else None
-            # (its cross-block float atomics are order-dependent: under torch.use_deterministic_algorithms the GEMM route,
-            # deterministic like torchvision's, is taken instead)
             if need_w and x.dtype == torch.float32 and not torch.are_deterministic_algorithms_enabled() \
                     and lib.devis_dcn_wgrad_supported(c, cout, kh, kw, _DTYPES[x.dtype]):
-                # narrow layers: gather + contraction with grad_out in one kernel, no column matrix (dcn_wgrad_kernel)
+                # narrow layers: gather + contraction with grad_out in one kernel, no column matrix (dcn_wgrad_kernel).
+                # Its cross-block float atomics are order-dependent: under torch.use_deterministic_algorithms the GEMM
+                # route below, deterministic like torchvision's, is taken instead.
                 gw3 = torch.empty((cout, k, c), dtype=x.dtype, device=x.device)
                 _lib.check(lib.devis_dcn_weight_grad(_ptr(x), _ptr(offset), _ptr(mask), _ptr(g), _ptr(gw3), *ctx.dims,
                                                      cout, stream))
