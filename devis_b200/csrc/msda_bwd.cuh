@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);
         const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
         const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
         float *gloc = reinterpret_cast<float *>(a.seg[sg].grad_loc);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
             const bool klive = k < K;
-            const int4 sl = s_slot[slot_base + (klive ? k / P : 0)];
+            const int4 sl = s_slot[slot_base + (klive ? div_p(k, P, pshift) : 0)];
 #pragma unroll
             for (int i = 0; i < QPG; ++i) {
                 const size_t row = ((size_t)outer * Lq + q[i]) * M + m;

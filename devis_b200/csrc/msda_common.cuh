@@ -85,6 +85,16 @@ __device__ __forceinline__ void build_slots(int4 *s_slot, const ClipTable &tb, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// k / P and slot % L with RUNTIME P and L: an integer division costs ~20 instructions in kernels that
+// are bound by instruction issue (forward: 59 % issue-active with 6 warps per scheduler); points per
+// slot and levels are powers of two in every DeVIS configuration (4 and 4), so take shifts and masks
+// there and keep the division for the rest.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pow2_shift(int v) { return (v > 0 && (v & (v - 1)) == 0) ? __ffs(v) - 1 : -1; }
+__device__ __forceinline__ int div_p(int k, int P, int pshift) { return pshift >= 0 ? (k >> pshift) : (k / P); }
+__device__ __forceinline__ int mod_l(int s, int L, int lshift) { return lshift >= 0 ? (s & (L - 1)) : (s % L); }
+
+// ---------------------------------------------------------------------------------------------
 // One tap's geometry, computed by ONE lane and then handed to the lanes that own the channels.
 // Mirrors cuda/ms_deform_im2col_cuda.cuh:281-288 (pixel coordinate and range test) and :38-52,80
 // (floor cell, bilinear weights); the rounding sequence of the coordinate is the reference's:

@@ -82,13 +82,13 @@ __global__ void __launch_bounds__(256, DEVIS_FWD_MIN_BLOCKS) msda_fwd_kernel(con
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);
         const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
         const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
             const bool klive = k < K;
-            const int4 sl = s_slot[slot_base + (klive ? k / P : 0)];
+            const int4 sl = s_slot[slot_base + (klive ? div_p(k, P, pshift) : 0)];
 #pragma unroll
             for (int i = 0; i < QPG; ++i) {
                 const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
@@ -283,11 +283,11 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
     TapIn nxt[QPG];
     load_taps(0, 0, nxt);
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;   // P % 4 == 0, hence K % 4 == 0
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);   // P % 4 == 0, hence K % 4 == 0
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
             const bool klive = k < K;
-            const int4 sl = s_slot[slot_base + (klive ? k / P : 0)];
+            const int4 sl = s_slot[slot_base + (klive ? div_p(k, P, pshift) : 0)];
             const unsigned my_pitch = (unsigned)sl.y * rowbytes;
             const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);   // slot of taps k0 .. k0+3
             const unsigned pitch_hi = __shfl_sync(0xffffffffu, my_pitch, 4, 8);   // slot of taps k0+4 .. k0+7
@@ -435,12 +435,12 @@ __global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P;   // P % 4 == 0 (checked by the launcher)
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);   // P % 4 == 0 (checked by the launcher)
         const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
         const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;                                // always < K
-            const int4 sl = s_slot[slot_base + k0 / P];          // one slot for the whole exchange
+            const int4 sl = s_slot[slot_base + div_p(k0, P, pshift)];          // one slot for the whole exchange
             const unsigned pitch = (unsigned)sl.y * rowbytes;    // bytes between vertically adjacent rows
 #pragma unroll
             for (int i = 0; i < QPG; ++i) {

@@ -113,7 +113,7 @@ __device__ __forceinline__ RawTap load_raw_tap(const FusedArgs &a, int sg, size_
     r.lg = 0.f;
     const int P = a.P[sg], K = a.n_slots[sg] * P;
     if (live && k < K) {
-        const int level = (k / P) % a.src.L;
+        const int level = mod_l(div_p(k, P, pow2_shift(P)), a.src.L, pow2_shift(a.src.L));
         r.off = ld_stream_f2(reinterpret_cast<const float2 *>(a.off[sg] + row * K * 2) + k);
         r.rf = __ldg(reinterpret_cast<const float2 *>(a.ref + (qrow * a.src.L + (sg == 0 ? level : 0)) * 2));
         r.lg = __ldg(a.logit[sg] + row * K + k);      // in L1 since row_softmax_stats
@@ -172,11 +172,11 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
     for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, 0, row[i], qrow[i], j, qlive[i]);
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.P[sg], K = a.n_slots[sg] * P;             // P % 4 == 0 (checked by the launcher)
+        const int P = a.P[sg], K = a.n_slots[sg] * P, pshift = pow2_shift(P);   // P % 4 == 0 (checked by the launcher)
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
             const bool klive = k < K;
-            const int ls = klive ? k / P : 0;                      // slot within the segment
+            const int ls = klive ? div_p(k, P, pshift) : 0;        // slot within the segment
             const int4 sl = s_slot[slot_base + ls];
             const unsigned my_pitch = (unsigned)sl.y * rowbytes;
             const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);
@@ -249,10 +249,10 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.P[sg], K = a.n_slots[sg] * P;             // P % 4 == 0: one slot per exchange, k < K always
+        const int P = a.P[sg], K = a.n_slots[sg] * P, pshift = pow2_shift(P);   // P % 4 == 0: one slot per exchange, k < K always
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
-            const int4 sl = s_slot[slot_base + k0 / P];
+            const int4 sl = s_slot[slot_base + div_p(k0, P, pshift)];
             const unsigned pitch = (unsigned)sl.y * rowbytes;
             // loaded at use: with 8 groups per warp a prefetch one exchange ahead does not pay here (531 vs 524 us; the
             // same holds for msda_fwd8_kernel, 431 vs 403 us)
@@ -327,13 +327,13 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
     int slot_base = 0, parity = 0, it = 0;
     RawTap nxt = load_raw_tap(a, 0, row, qrow, j, qlive);
     for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.P[sg], K = a.n_slots[sg] * P;
+        const int P = a.P[sg], K = a.n_slots[sg] * P, pshift = pow2_shift(P);
         float *goff = a.grad_off[sg] + row * K * 2;
         float *glog = a.grad_logit[sg] + row * K;
         for (int k0 = 0; k0 < K; k0 += LPG) {
             const int k = k0 + j;
             const bool live = k < K && qlive;
-            const int ls = live ? k / P : 0;
+            const int ls = live ? div_p(k, P, pshift) : 0;
             const int4 sl = s_slot[slot_base + ls];
             const RawTap cur = nxt;
             if (k0 + LPG < K) nxt = load_raw_tap(a, sg, row, qrow, k + LPG, qlive);
