@@ -1,7 +1,8 @@
 // msda_bwd_sort.cuh -- whole-clip backward with per-block SORTED pre-aggregation of grad_value (encoder form).
 //
-// msda_bwd_kernel runs at the rate at which reductions can LEAVE an SM (5.2 cycles per 128-byte row for
-// red.global.add.v4.f32, benchmarks/micro/smem_accumulate.cu), and in the encoder most of those rows are duplicates: the
+// msda_bwd_kernel is co-limited by the rate at which reductions can LEAVE an SM (5.2 cycles per 128-byte row for
+// red.global.add.v4.f32, benchmarks/micro/smem_accumulate.cu; 79 % busy) and the L1 data pipe, and in the encoder most of
+// those rows are duplicates: the
 // 64 pixel-queries of an 8 x 8 tile sample the same few hundred rows of every (frame, level) map.  Shared-memory float
 // atomics are CAS loops on sm_100a and fixed-point integer windows cost 16 ATOMS per lane and tap (msda_bwd_win.cuh,
 // slower than the direct scatter), so the duplicates are merged by SORTING instead:

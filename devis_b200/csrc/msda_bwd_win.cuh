@@ -1,6 +1,6 @@
 // msda_bwd_win.cuh -- whole-clip backward with per-block pre-aggregation of grad_value (encoder form).
 //
-// msda_bwd_kernel runs at the rate at which reductions can LEAVE an SM (5.3 cycles per 128-byte row for
+// msda_bwd_kernel is limited by the rate at which reductions can LEAVE an SM (5.3 cycles per 128-byte row for
 // red.global.add.v4.f32, benchmarks/micro/smem_accumulate.cu), and in the encoder most of those rows are duplicates:
 // the 64 pixel-queries of an 8 x 8 tile sample the same few hundred rows of the coarser levels of every frame.
 // Shared-memory FLOAT atomics are CAS loops on sm_100a (14 cycles per row), but shared-memory INTEGER atomics are
