@@ -52,4 +52,5 @@ def main():
 
 
 if __name__ == "__main__":
+    os.environ["DEVIS_MSDA_TUNING"] = "1"      # developer knobs (devis_msda_set_tuning) are inert without it
     main()

@@ -6,6 +6,8 @@ import sys
 
 import torch
 
+os.environ["DEVIS_MSDA_TUNING"] = "1"      # developer knobs (devis_msda_set_tuning) are inert without it
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from benchmarks.sweep import RawClip  # noqa: E402
 from devis_b200 import _lib, clip_geometry, synthetic  # noqa: E402

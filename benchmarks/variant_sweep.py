@@ -30,6 +30,6 @@ ap.add_argument("--dist", default="local")
 a = ap.parse_args()
 libs = sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so")))
 for lib in [os.path.join(ROOT, "devis_b200", "libdevis_msda.so")] + libs:
-    env = dict(os.environ, DEVIS_MSDA_LIB=lib)
+    env = dict(os.environ, DEVIS_MSDA_LIB=lib, DEVIS_MSDA_TUNING="1")
     r = subprocess.run([sys.executable, "-c", CHILD, a.kind, a.dtype, a.dist], env=env, capture_output=True, text=True)
     print(f"{os.path.basename(lib):28s} {a.kind} {a.dtype} {a.dist}  us by threads: {r.stdout.strip()} {r.stderr.strip()[-200:] if r.returncode else ''}", flush=True)

@@ -12,9 +12,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DEVIS_MSDA_LIB selects another build of the same ABI (kernel A/B experiments); the default is the in-tree library
 LIB_PATH = os.environ.get("DEVIS_MSDA_LIB") or os.path.join(_HERE, "libdevis_msda.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, F64, BF16 = 0, 1, 2
 FLAG_DETERMINISTIC, FLAG_NO_GRAD_VALUE, FLAG_BF16_GRAD_VALUE = 1, 2, 4
+# temporal_ref_mode of the fused-prologue entry points (DEVIS_TMSDA_TREF_*)
+TREF_LEVEL0, TREF_OWN, TREF_SAMPLED = 0, 1, 2
+# kernel families of devis_msda_kernel_launches (DEVIS_MSDA_KERNEL_*)
+KERNEL_FWD_GROUPED, KERNEL_FWD_GENERIC, KERNEL_BWD_GROUPED, KERNEL_BWD_GENERIC = 0, 1, 2, 3
+KERNEL_FUSED_FWD, KERNEL_FUSED_BWD, KERNEL_BWD_SORTED, KERNEL_AUX, KERNEL_DCN = 4, 5, 6, 7, 8
 
 _vp, _i, _u, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
 
@@ -24,6 +29,7 @@ SIGNATURES = {
     "devis_msda_error_string": (ctypes.c_char_p, [_i]),
     "devis_msda_last_cuda_error": (_i, []),
     "devis_msda_launch_count": (ctypes.c_uint64, []),
+    "devis_msda_kernel_launches": (ctypes.c_uint64, [_i]),
     "devis_msda_set_tuning": (_i, [_i, _i]),
     "devis_msda_forward": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "devis_msda_backward_workspace_bytes": (_sz, [_i] * 8 + [_u]),
@@ -31,8 +37,8 @@ SIGNATURES = {
     "devis_tmsda_forward": (_i, [_vp] * 10 + [_i] * 10 + [_vp]),
     "devis_tmsda_backward_workspace_bytes": (_sz, [_i] * 10 + [_u]),
     "devis_tmsda_backward": (_i, [_vp] * 15 + [_i] * 10 + [_u, _vp, _sz, _vp]),
-    "devis_tmsda_fused_forward": (_i, [_vp] * 11 + [_i] * 10 + [_vp]),
-    "devis_tmsda_fused_backward": (_i, [_vp] * 16 + [_i] * 10 + [_u, _vp]),
+    "devis_tmsda_fused_forward": (_i, [_vp] * 15 + [_i] * 12 + [_vp]),
+    "devis_tmsda_fused_backward": (_i, [_vp] * 17 + [_i] * 12 + [_u, _vp]),
     # include/devis_deform_conv.h
     "devis_dcn_im2col": (_i, [_vp] * 4 + [_i] * 15 + [_vp]),
     "devis_dcn_col2im": (_i, [_vp] * 7 + [_i] * 15 + [_vp]),
@@ -86,5 +92,11 @@ def launch_count():
     return int(load().devis_msda_launch_count())
 
 
+def kernel_launches(family):
+    """launches of one kernel family (KERNEL_*) so far: which kernel served a call, not just that one ran"""
+    return int(load().devis_msda_kernel_launches(int(family)))
+
+
 def set_tuning(key, value):
+    """developer knob of the benchmarks; the library refuses it unless the process runs with DEVIS_MSDA_TUNING=1"""
     check(load().devis_msda_set_tuning(int(key), int(value)))

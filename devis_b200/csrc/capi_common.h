@@ -5,4 +5,5 @@
 #include <cuda_runtime.h>
 
 int devis_capi_cuda_fail(cudaError_t e);
-int devis_capi_check_launch();
+int devis_capi_check_launch(int family);   // family: DEVIS_MSDA_KERNEL_* (include/devis_msda.h)
+int devis_capi_helper_blocks();            // 8 blocks per SM of the current device, for grid-stride helper kernels

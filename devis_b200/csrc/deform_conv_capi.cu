@@ -43,7 +43,7 @@ int dispatch(const DcnDims &d, int dtype, F4 f4, F8 f8, S8 s8, S32 s32)
             if (G == 32) s32(grid, n0);
             else s8(grid, n0);
         }
-        const int rc = devis_capi_check_launch();
+        const int rc = devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);
         if (rc) return rc;
     }
     return DEVIS_MSDA_OK;
@@ -153,12 +153,19 @@ FusedPlan fused_plan(int C, int cout, int kh, int kw, int dtype)
     return p;
 }
 
-// the one constant bank is shared by every stream of the process: calls are serialised by a mutex on the host and by an
-// event on the device (a call on another stream waits for the previous call's kernels before it overwrites the bank)
+// the constant bank exists once PER DEVICE and is shared by every stream using that device: calls are serialised by a
+// mutex on the host and, per device, by an event (a call on another stream waits for the previous call's kernels before
+// it overwrites the bank).  State is indexed by the current device, so single-process multi-GPU callers
+// (nn.DataParallel, per-thread devices) never record an event created on another device.
+// Stream capture: the cross-stream guard cannot be recorded into a graph, so a captured call is only safe when no eager
+// call on ANOTHER stream of the same device touches the bank while the graph replays.
+constexpr int kMaxDevices = 64;
 std::mutex g_const_mutex;
-cudaEvent_t g_const_event = nullptr;
-cudaStream_t g_const_stream = nullptr;
-bool g_const_used = false;
+struct ConstBankState {
+    cudaEvent_t event = nullptr;
+    cudaStream_t stream = nullptr;
+    bool used = false;
+} g_const[kMaxDevices];
 
 bool stream_is_capturing(cudaStream_t st)
 {
@@ -200,14 +207,14 @@ int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int ou
         const unsigned blocks = (unsigned)((p.lanes_elems + 255) / 256 > 1184 ? 1184 : (p.lanes_elems + 255) / 256);
         dcn_pack_weight_kernel<<<blocks, 256, 0, st>>>((const float *)weight, (float *)packed, out_channels, channels, K,
                                                        p.G, nblk);
-        const int rc = devis_capi_check_launch();
+        const int rc = devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);
         if (rc) return rc;
     }
     if (p.const_elems) {
         const unsigned blocks = (unsigned)((p.const_elems + 255) / 256 > 1184 ? 1184 : (p.const_elems + 255) / 256);
         dcn_pack_weight_const_kernel<<<blocks, 256, 0, st>>>((const float *)weight, (float *)packed + p.lanes_elems,
                                                              out_channels, channels, K, p.CT);
-        const int rc = devis_capi_check_launch();
+        const int rc = devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);
         if (rc) return rc;
     }
     return DEVIS_MSDA_OK;
@@ -219,7 +226,7 @@ int devis_dcn_pack_weight(const void *weight, void *packed, int channels, int ou
         const dim3 grid((unsigned)((d.Wo + (32 / G) * PPG - 1) / ((32 / G) * PPG)), (unsigned)((d.Ho + 7) / 8), \
                         (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));                            \
         KERNEL<COUT, G, PPG><<<grid, 256, 0, st>>>(__VA_ARGS__, d, n0);                                      \
-        const int rc_ = devis_capi_check_launch();                                                           \
+        const int rc_ = devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);                                                           \
         if (rc_) return rc_;                                                                                 \
     }
 #define DCN_FUSED_CASES(KERNEL, G, PPG, ...)                                     \
@@ -270,13 +277,20 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
             if (e != cudaSuccess) return devis_capi_cuda_fail(e);
         }
         const bool capturing = stream_is_capturing(st);
+        int dev = 0;
+        {
+            const cudaError_t e = cudaGetDevice(&dev);
+            if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+            if (dev < 0 || dev >= kMaxDevices) return DEVIS_MSDA_ERR_UNSUPPORTED;
+        }
+        ConstBankState &bank = g_const[dev];
         if (!capturing) {
-            if (!g_const_event) {
-                const cudaError_t e = cudaEventCreateWithFlags(&g_const_event, cudaEventDisableTiming);
+            if (!bank.event) {
+                const cudaError_t e = cudaEventCreateWithFlags(&bank.event, cudaEventDisableTiming);
                 if (e != cudaSuccess) return devis_capi_cuda_fail(e);
             }
-            if (g_const_used && g_const_stream != st) {
-                const cudaError_t e = cudaStreamWaitEvent(st, g_const_event, 0);
+            if (bank.used && bank.stream != st) {
+                const cudaError_t e = cudaStreamWaitEvent(st, bank.event, 0);
                 if (e != cudaSuccess) return devis_capi_cuda_fail(e);
             }
         }
@@ -291,16 +305,16 @@ int devis_dcn_fused_forward(const void *input, const void *offset, const void *m
                     const dim3 grid((unsigned)((d.Wo + kDcnCTileW - 1) / kDcnCTileW), (unsigned)((d.Ho + kDcnCTileH - 1) / kDcnCTileH),
                                     (unsigned)(d.N - n0 < kMaxGridZ ? d.N - n0 : kMaxGridZ));
                     kernel<<<grid, 256, smem, st>>>(in, of, mk, bs, o, d, n0, out_channels, CT * t, k0, k1);
-                    const int rc_ = devis_capi_check_launch();
+                    const int rc_ = devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);
                     if (rc_) return rc_;
                 }
             }
         }
         if (!capturing) {
-            const cudaError_t e = cudaEventRecord(g_const_event, st);
+            const cudaError_t e = cudaEventRecord(bank.event, st);
             if (e != cudaSuccess) return devis_capi_cuda_fail(e);
-            g_const_used = true;
-            g_const_stream = st;
+            bank.used = true;
+            bank.stream = st;
         }
         return DEVIS_MSDA_OK;
     }
@@ -375,7 +389,7 @@ int devis_dcn_weight_grad(const void *input, const void *offset, const void *mas
     const int G = channels / 4, gpb = 256 / G;
     // pixels per lane group: long runs amortise the block reduction, but keep >= ~4 blocks per SM in flight
     int run = 64;
-    while (run > 8 && ((plane + (long long)gpb * run - 1) / ((long long)gpb * run)) * kernel_h * kernel_w * batch < 148 * 8) run /= 2;
+    while (run > 8 && ((plane + (long long)gpb * run - 1) / ((long long)gpb * run)) * kernel_h * kernel_w * batch < devis_capi_helper_blocks()) run /= 2;
     const unsigned gx = (unsigned)((plane + (long long)gpb * run - 1) / ((long long)gpb * run));
     const float *in = (const float *)input, *of = (const float *)offset, *mk = (const float *)mask, *go = (const float *)grad_out;
     float *gw = (float *)grad_weight;
@@ -396,7 +410,7 @@ int devis_dcn_weight_grad(const void *input, const void *offset, const void *mas
         }
 #undef DCN_WGRAD_G
 #undef DCN_WGRAD
-        const int rc2 = devis_capi_check_launch();
+        const int rc2 = devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);
         if (rc2) return rc2;
     }
     return DEVIS_MSDA_OK;

@@ -4,11 +4,11 @@
 // (cuda/ms_deform_attn_cuda.cu:28-52,93-119), picks a kernel, launches on the caller's stream and
 // reports launch failures as error codes.  No torch types, no allocation, no synchronisation.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/devis_msda.h"
 #include "msda_bwd.cuh"
-#include "msda_bwd_win.cuh"
 #include "msda_bwd_sort.cuh"
 #include "msda_common.cuh"
 #include "msda_fwd.cuh"
@@ -22,10 +22,46 @@ using namespace devis;
 namespace {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_family_launches[DEVIS_MSDA_KERNEL_FAMILIES];
 thread_local int t_last_cuda_error = 0;
-std::atomic<int> g_tuning[16];
+
+// Launch-shape knobs of the developer benchmarks (benchmarks/sweep.py, variant A/B runs).  They only exist when the
+// process was started with DEVIS_MSDA_TUNING=1: a product process cannot have its kernel selection changed behind its
+// back (devis_msda_set_tuning returns DEVIS_MSDA_ERR_UNSUPPORTED), and every key then reads 0 = built-in heuristic.
+std::atomic<int> g_tuning_store[16];
+bool tuning_enabled()
+{
+    static const bool on = [] {
+        const char *e = std::getenv("DEVIS_MSDA_TUNING");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+struct TuningView {
+    struct Key {
+        int k;
+        int load() const { return tuning_enabled() ? g_tuning_store[k].load() : 0; }
+    };
+    Key operator[](int k) const { return Key{k}; }
+} g_tuning;
 
 }  // namespace
+
+// grid of the grid-stride helper kernels: 8 blocks per SM of the CURRENT device (queried once per device)
+int devis_capi_helper_blocks()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 8;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        v = sms * 8;
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 
 // shared with the other translation units of the library (capi_common.h)
 int devis_capi_cuda_fail(cudaError_t e)
@@ -34,9 +70,10 @@ int devis_capi_cuda_fail(cudaError_t e)
     return DEVIS_MSDA_ERR_CUDA;
 }
 
-int devis_capi_check_launch()
+int devis_capi_check_launch(int family)
 {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (family >= 0 && family < DEVIS_MSDA_KERNEL_FAMILIES) g_family_launches[family].fetch_add(1, std::memory_order_relaxed);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DEVIS_MSDA_OK : devis_capi_cuda_fail(e);
 }
@@ -44,7 +81,7 @@ int devis_capi_check_launch()
 namespace {
 
 int cuda_fail(cudaError_t e) { return devis_capi_cuda_fail(e); }
-int check_launch() { return devis_capi_check_launch(); }
+int check_launch(int family) { return devis_capi_check_launch(family); }
 
 size_t elem_size(int dtype) { return dtype == DEVIS_MSDA_F64 ? 8 : dtype == DEVIS_MSDA_BF16 ? 2 : 4; }
 
@@ -122,7 +159,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
             else DEVIS_FWD8(false, 1);
         }
 #undef DEVIS_FWD8
-        return check_launch();
+        return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
     }
     // 8 lanes x 4 channels with 16-byte tap records (msda_fwdc_kernel), D = 32 and P % 4 == 0: -4..5 % against the
     // 32-byte records for fp32 value (default for fp32).  Tuning key 5: 1 always, 2 never.
@@ -145,7 +182,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
             else if (s.qpg == 2) msda_fwdc_kernel<false, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
             else msda_fwdc_kernel<false, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
         }
-        return check_launch();
+        return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
     }
     if (lpg) {
         const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 4, 0, 1);
@@ -170,7 +207,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
         }
 #undef DEVIS_FWD_Q
 #undef DEVIS_FWD
-        return check_launch();
+        return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
     }
     const int threads = 128, wpc = threads / 32;
     const long long blocks = ((long long)d.Lq * d.M + wpc - 1) / wpc;
@@ -179,7 +216,7 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     if (dtype == DEVIS_MSDA_F32) msda_fwd_generic_kernel<float, SlotSrc><<<grid, threads, smem, st>>>(a);
     else if (dtype == DEVIS_MSDA_F64) msda_fwd_generic_kernel<double, SlotSrc><<<grid, threads, smem, st>>>(a);
     else msda_fwd_generic_kernel<__nv_bfloat16, SlotSrc><<<grid, threads, smem, st>>>(a);
-    return check_launch();
+    return check_launch(DEVIS_MSDA_KERNEL_FWD_GENERIC);
 }
 
 // deterministic-mode workspace: [int64 accumulators: outer*S*M*D][2 x u32 max slots, padded to 16 B]
@@ -188,11 +225,11 @@ size_t det_workspace_bytes(long long outer, long long S, long long M, long long 
     return (size_t)(outer * S * M * D) * sizeof(long long) + 16;
 }
 
-// sorted whole-clip backward (msda_bwd_sort.cuh), defined below
-bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, bool det);
-int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, bool det, cudaStream_t st);
-inline bool sort_applicable(const BwdArgs<DeviceLevels> &, int, unsigned, bool) { return false; }
-inline int launch_backward_sort(const BwdArgs<DeviceLevels> &, int, bool, cudaStream_t) { return DEVIS_MSDA_ERR_UNSUPPORTED; }
+// sorted deterministic whole-clip backward (msda_bwd_sort.cuh), defined below
+bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags);
+int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, cudaStream_t st);
+inline bool sort_applicable(const BwdArgs<DeviceLevels> &, int, unsigned) { return false; }
+inline int launch_backward_sort(const BwdArgs<DeviceLevels> &, int, cudaStream_t) { return DEVIS_MSDA_ERR_UNSUPPORTED; }
 
 template <class SlotSrc>
 int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
@@ -216,15 +253,15 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
         a.det.max_bits = slots;
         if (d.outer > 0 && d.Lq > 0) {
             const size_t n_go = (size_t)d.outer * d.Lq * d.M * d.D;
-            const int blocks = 148 * 8;
+            const int blocks = devis_capi_helper_blocks();
             if (dtype == DEVIS_MSDA_BF16) absmax_kernel<true><<<blocks, 256, 0, st>>>(a.grad_out, n_go, slots);
             else absmax_kernel<false><<<blocks, 256, 0, st>>>(a.grad_out, n_go, slots);
-            int rc = check_launch();
+            int rc = check_launch(DEVIS_MSDA_KERNEL_AUX);
             if (rc) return rc;
             for (int sg = 0; sg < a.n_seg; ++sg) {
                 const size_t n_aw = (size_t)d.outer * d.Lq * d.M * a.seg[sg].n_slots * a.seg[sg].P;
                 absmax_kernel<false><<<blocks, 256, 0, st>>>(a.seg[sg].aw, n_aw, slots + 1);
-                rc = check_launch();
+                rc = check_launch(DEVIS_MSDA_KERNEL_AUX);
                 if (rc) return rc;
             }
         }
@@ -240,15 +277,15 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
     const int lpg = lanes_per_group(dtype, d);
     auto finalize = [&]() -> int {
         if (!det || n_value == 0) return DEVIS_MSDA_OK;
-        det_finalize_kernel<<<148 * 8, 256, 0, st>>>(a.det.acc, final_grad_value, n_value, a.det.max_bits, lpg);
-        return check_launch();
+        det_finalize_kernel<<<devis_capi_helper_blocks(), 256, 0, st>>>(a.det.acc, final_grad_value, n_value, a.det.max_bits, lpg);
+        return check_launch(DEVIS_MSDA_KERNEL_AUX);
     };
     if (d.outer == 0 || d.Lq == 0) return finalize();
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
-    if (lpg && det && sort_applicable(a, dtype, flags, true)) {
+    if (lpg && det && sort_applicable(a, dtype, flags)) {
         // deterministic mode, encoder form: sorted pre-aggregation in 64-bit fixed point (bit-identical to the direct
         // deterministic scatter, ~4x faster: 5x fewer 64-bit reductions leave the SM)
-        const int rc = launch_backward_sort(a, dtype, true, st);
+        const int rc = launch_backward_sort(a, dtype, st);
         return rc ? rc : finalize();
     }
     if (lpg) {
@@ -276,7 +313,7 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
         }
 #undef DEVIS_BWD_Q
 #undef DEVIS_BWD
-        const int rc = check_launch();
+        const int rc = check_launch(DEVIS_MSDA_KERNEL_BWD_GROUPED);
         return rc ? rc : finalize();
     }
     const int threads = 128, wpc = threads / 32;
@@ -286,96 +323,21 @@ int launch_backward(BwdArgs<SlotSrc> a, int dtype, unsigned flags, void *workspa
     if (dtype == DEVIS_MSDA_F32) msda_bwd_generic_kernel<float, SlotSrc><<<grid, threads, smem, st>>>(a);
     else if (dtype == DEVIS_MSDA_F64) msda_bwd_generic_kernel<double, SlotSrc><<<grid, threads, smem, st>>>(a);
     else msda_bwd_generic_kernel<__nv_bfloat16, SlotSrc><<<grid, threads, smem, st>>>(a);
-    const int rc = check_launch();
+    const int rc = check_launch(DEVIS_MSDA_KERNEL_BWD_GENERIC);
     return rc ? rc : finalize();
 }
 
-// ---- windowed whole-clip backward (msda_bwd_win.cuh) -----------------------------------------------------------
-constexpr size_t kWinWorkspaceBytes = 16;   // [u32 unused][u32 bits of max|attn weight|]
-
-size_t window_smem_bytes(int n_slots_total, int budget_rows)
+// ---- sorted deterministic whole-clip backward (msda_bwd_sort.cuh) ------------------------------------------------
+// Serves the deterministic mode of the encoder form: one query per pyramid pixel (the caller says so by passing a
+// query_order), D = 32, fp32 / bf16 value, levels stored back to back, an even number of levels, 4 points per slot.
+// ~4x faster than the direct 64-bit scatter and bit-identical to it.  (The float variant of the same scheme lost to the
+// direct float scatter -- data-pipe bound, DESIGN.md section 7 -- and is no longer built; benchmarks/experimental keeps
+// the round-1 windowed kernel for the record.)  Developer keys: 6 = 1 forces the direct scatter, 7 = window margin in
+// pixels (default 6), 9 = first level with a window + 1 (default: all levels).
+bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags)
 {
-    return (size_t)n_slots_total * sizeof(int4) + 5 * kMaxLevels * sizeof(int) + 16 +
-           (size_t)(kWinThreads / 32) * (TapExchange<8>::kBytesPerWarp + 64 * sizeof(unsigned)) +
-           (size_t)budget_rows * 32 * sizeof(int);
-}
-
-// The windowed kernel serves the encoder form: one query per pyramid pixel (the caller says so by passing a
-// query_order), D = 32, fp32 / bf16 value with float grad_value, levels stored back to back, every sampled frame's
-// taps a whole number of 8-tap chunks.  EXPERIMENTAL and off by default (tuning key 6 = 2 switches it on): at the DeVIS
-// shape it removes 34 - 41 % of the global reductions but executes 33 % more instructions and keeps the L1 data pipe at
-// 71 %, so it runs in 1.76 ms against 1.43 ms for msda_bwd_kernel (profiles/README.md, round 1h).
-bool window_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, const void *workspace, size_t workspace_bytes)
-{
-    if (g_tuning[6].load() != 2) return false;
-    if (!a.q_perm || !a.grad_value || (flags & (DEVIS_MSDA_FLAG_DETERMINISTIC | DEVIS_MSDA_FLAG_BF16_GRAD_VALUE))) return false;
-    if (!workspace || workspace_bytes < kWinWorkspaceBytes) return false;
-    if (lanes_per_group(dtype, a.d) != 8 || a.d.Lq != a.d.S || a.d.outer == 0) return false;
-    const ClipTable &tb = a.src;
-    int next = 0;
-    for (int l = 0; l < tb.L; ++l) {
-        if (tb.lsi[l] != next) return false;
-        next += tb.H[l] * tb.W[l];
-    }
-    if (next != a.d.S) return false;
-    for (int sg = 0; sg < a.n_seg; ++sg)
-        if ((tb.L * a.seg[sg].P) % 8 != 0 || a.seg[sg].n_slots % tb.L != 0) return false;
-    return true;
-}
-
-int launch_backward_window(const BwdArgs<ClipTable> &a, int dtype, void *workspace, cudaStream_t st)
-{
-    const OpDims &d = a.d;
-    WinArgs w{};
-    w.b = a;
-    int tiles = 0;
-    for (int l = 0; l < a.src.L; ++l) {
-        w.tiles_x[l] = (a.src.W[l] + kWinTile - 1) / kWinTile;
-        w.tile_start[l] = tiles;
-        tiles += w.tiles_x[l] * ((a.src.H[l] + kWinTile - 1) / kWinTile);
-    }
-    w.n_tiles = tiles;
-    w.margin = g_tuning[7].load() > 0 ? g_tuning[7].load() : 6;
-    w.budget_rows = g_tuning[8].load() > 0 ? g_tuning[8].load() : 384;
-    if (w.budget_rows > 1536) w.budget_rows = 1536;
-    unsigned *slots = reinterpret_cast<unsigned *>(workspace);
-    w.aw_max_bits = slots + 1;
-    cudaError_t e = cudaMemsetAsync(workspace, 0, kWinWorkspaceBytes, st);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaMemsetAsync(a.grad_value, 0, (size_t)d.outer * d.S * d.M * d.D * sizeof(float), st);
-    if (e != cudaSuccess) return cuda_fail(e);
-    for (int sg = 0; sg < a.n_seg; ++sg) {
-        const size_t n_aw = (size_t)d.outer * d.Lq * d.M * a.seg[sg].n_slots * a.seg[sg].P;
-        absmax_kernel<false><<<148 * 8, 256, 0, st>>>(a.seg[sg].aw, n_aw, slots + 1);
-        const int rc = check_launch();
-        if (rc) return rc;
-    }
-    const size_t smem = window_smem_bytes(a.n_slots_total, w.budget_rows);
-    const dim3 grid((unsigned)(tiles * d.M), (unsigned)d.outer);
-    if (dtype == DEVIS_MSDA_BF16) {
-        e = cudaFuncSetAttribute(msda_bwdw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e);
-        msda_bwdw_kernel<true><<<grid, kWinThreads, smem, st>>>(w);
-    } else {
-        e = cudaFuncSetAttribute(msda_bwdw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e);
-        msda_bwdw_kernel<false><<<grid, kWinThreads, smem, st>>>(w);
-    }
-    return check_launch();
-}
-
-// ---- sorted whole-clip backward (msda_bwd_sort.cuh) ---------------------------------------------------------------
-// Serves the encoder form: one query per pyramid pixel (the caller says so by passing a query_order), D = 32, fp32 /
-// bf16 value with float grad_value, levels stored back to back, an even number of levels, 4 points per slot.
-// Default mode: slower than the direct scatter (data-pipe bound) -> opt-in, tuning key 6 = 3.
-// Deterministic mode: ~4x faster than the direct 64-bit scatter and bit-identical to it -> on unless key 6 = 1.
-// Key 7 = window margin in pixels (default 6); key 9 = first level with a window + 1 (default: all levels).
-bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, bool det)
-{
-    const int mode = g_tuning[6].load();
-    if (det ? mode == 1 : mode != 3) return false;          // deterministic mode: on by default; else opt-in
-    if (det ? !a.det.acc : (!a.grad_value || (flags & DEVIS_MSDA_FLAG_DETERMINISTIC))) return false;
-    if (!a.q_perm || (flags & DEVIS_MSDA_FLAG_BF16_GRAD_VALUE)) return false;
+    if (g_tuning[6].load() == 1) return false;
+    if (!a.det.acc || !a.q_perm || (flags & DEVIS_MSDA_FLAG_BF16_GRAD_VALUE)) return false;
     if (lanes_per_group(dtype, a.d) != 8 || a.d.Lq != a.d.S || a.d.outer == 0) return false;
     const ClipTable &tb = a.src;
     if (tb.L % 2 != 0) return false;
@@ -391,17 +353,17 @@ bool sort_applicable(const BwdArgs<ClipTable> &a, int dtype, unsigned flags, boo
     return true;
 }
 
-template <bool BF, bool DET>
+template <bool BF>
 int launch_sort_kernel(const SortArgs &w, dim3 grid, size_t smem, cudaStream_t st)
 {
-    const cudaError_t e = cudaFuncSetAttribute(msda_bwds_kernel<BF, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t e = cudaFuncSetAttribute(msda_bwds_kernel<BF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e);
-    msda_bwds_kernel<BF, DET><<<grid, kSortThreads, smem, st>>>(w);
-    return check_launch();
+    msda_bwds_kernel<BF, true><<<grid, kSortThreads, smem, st>>>(w);
+    return check_launch(DEVIS_MSDA_KERNEL_BWD_SORTED);
 }
 
-// det: the caller (launch_backward) has set up a.det and zero-filled the accumulators, and runs the finalize pass
-int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, bool det, cudaStream_t st)
+// the caller (launch_backward) has set up a.det and zero-filled the accumulators, and runs the finalize pass
+int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, cudaStream_t st)
 {
     const OpDims &d = a.d;
     SortArgs w{};
@@ -416,15 +378,10 @@ int launch_backward_sort(const BwdArgs<ClipTable> &a, int dtype, bool det, cudaS
     w.margin = g_tuning[7].load() > 0 ? g_tuning[7].load() : 6;
     w.min_level = g_tuning[9].load() > 0 ? g_tuning[9].load() - 1 : 0;
     w.lut_entries = (a.src.L / 2) * kSortMaxKeys;
-    if (!det) {
-        const cudaError_t e = cudaMemsetAsync(a.grad_value, 0, (size_t)d.outer * d.S * d.M * d.D * sizeof(float), st);
-        if (e != cudaSuccess) return cuda_fail(e);
-    }
     const size_t smem = sort_smem_bytes(a.n_slots_total, w.lut_entries);
     if ((long long)tiles * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
     const dim3 grid((unsigned)(tiles * d.M), (unsigned)d.outer);
-    if (dtype == DEVIS_MSDA_BF16) return det ? launch_sort_kernel<true, true>(w, grid, smem, st) : launch_sort_kernel<true, false>(w, grid, smem, st);
-    return det ? launch_sort_kernel<false, true>(w, grid, smem, st) : launch_sort_kernel<false, false>(w, grid, smem, st);
+    return dtype == DEVIS_MSDA_BF16 ? launch_sort_kernel<true>(w, grid, smem, st) : launch_sort_kernel<false>(w, grid, smem, st);
 }
 
 int check_common(int outer, int S, int M, int D, int L, int Lq, int dtype)
@@ -484,10 +441,16 @@ const char *devis_msda_error_string(int code)
 int devis_msda_last_cuda_error(void) { return t_last_cuda_error; }
 uint64_t devis_msda_launch_count(void) { return g_launches.load(); }
 
+uint64_t devis_msda_kernel_launches(int family)
+{
+    return (family >= 0 && family < DEVIS_MSDA_KERNEL_FAMILIES) ? g_family_launches[family].load() : 0;
+}
+
 int devis_msda_set_tuning(int key, int value)
 {
     if (key < 0 || key >= 16) return DEVIS_MSDA_ERR_BAD_SHAPE;
-    g_tuning[key].store(value);
+    if (!tuning_enabled()) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    g_tuning_store[key].store(value);
     return DEVIS_MSDA_OK;
 }
 
@@ -593,8 +556,7 @@ size_t devis_tmsda_backward_workspace_bytes(int num_frames, int spatial_size, in
                                             int, int, int, int dtype, unsigned flags)
 {
     if ((flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE) || dtype == DEVIS_MSDA_F64) return 0;
-    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC))   // the experimental windowed kernel keeps max|attn weight| there
-        return g_tuning[6].load() == 2 ? kWinWorkspaceBytes : 0;
+    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC)) return 0;
     return det_workspace_bytes(num_frames, spatial_size, num_heads, channels);
 }
 
@@ -639,22 +601,22 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
     if (a.n_slots_total > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
     a.d = OpDims{num_frames, spatial_size, num_heads, channels, num_query};
     a.q_perm = query_order;
-    if (sort_applicable(a, dtype, flags, false)) return launch_backward_sort(a, dtype, false, (cudaStream_t)stream);
-    if (window_applicable(a, dtype, flags, workspace, workspace_bytes))
-        return launch_backward_window(a, dtype, workspace, (cudaStream_t)stream);
     return launch_backward(a, dtype, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, const int64_t *lsi, const int32_t *frames,
                       const void *ref, const void *off_c, const void *logit_c, const void *off_t, const void *logit_t,
-                      const int32_t *order, int T, int S, int M, int D, int L, int Lq, int Pc, int Pt, int Wt, int dtype)
+                      const int32_t *order, int T, int S, int M, int D, int L, int Lq, int Pc, int Pt, int Wt, int ref_dim,
+                      int tref_mode, int dtype)
 {
     int rc = check_common(T, S, M, D, L, Lq, dtype);
     if (rc) return rc;
-    if (Pc <= 0 || Pt < 0 || Wt < 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    if (Pc <= 0 || Pt < 0 || Wt < 0 || (ref_dim != 2 && ref_dim != 4) || tref_mode < 0 || tref_mode > 2)
+        return DEVIS_MSDA_ERR_BAD_SHAPE;
     if (dtype == DEVIS_MSDA_F64 || D != 32 || Pc % 4 != 0 || (Wt > 0 && Pt > 0 && Pt % 4 != 0))
         return DEVIS_MSDA_ERR_UNSUPPORTED;
     if ((unsigned long long)T * S * M * D * elem_size(dtype) >= (1ull << 32)) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    if ((unsigned long long)T * Lq * L >= (1ull << 31)) return DEVIS_MSDA_ERR_TOO_LARGE;   // ref rows are 31-bit
     const bool temporal = Wt > 0 && Pt > 0;
     if (!shapes || !lsi || (temporal && !frames)) return DEVIS_MSDA_ERR_NULL_POINTER;
     const bool empty = T == 0 || Lq == 0;
@@ -664,6 +626,8 @@ static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, co
     if (rc) return rc;
     a.value = value;
     a.ref = reinterpret_cast<const float *>(ref);
+    a.ref_dim = ref_dim;
+    a.tref_mode = tref_mode;
     a.off[0] = reinterpret_cast<const float *>(off_c);
     a.logit[0] = reinterpret_cast<const float *>(logit_c);
     a.off[1] = reinterpret_cast<const float *>(off_t);
@@ -672,6 +636,8 @@ static int fill_fused(FusedArgs &a, const void *value, const int64_t *shapes, co
     a.P[0] = Pc;
     a.n_slots[1] = temporal ? Wt * L : 0;
     a.P[1] = temporal ? Pt : 1;
+    a.inv_p[0] = 1.f / (float)Pc;
+    a.inv_p[1] = temporal ? 1.f / (float)Pt : 1.f;
     a.n_seg = temporal ? 2 : 1;
     if (a.n_slots[0] + a.n_slots[1] > kMaxSlots) return DEVIS_MSDA_ERR_TOO_LARGE;
     a.d = OpDims{T, S, M, D, Lq};
@@ -696,21 +662,38 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
                               const int64_t *level_start_index_host, const int32_t *frame_table_host,
                               const void *ref, const void *off_curr, const void *logit_curr,
                               const void *off_temporal, const void *logit_temporal, void *output,
+                              void *loc_curr_out, void *aw_curr_out, void *loc_temporal_out, void *aw_temporal_out,
                               const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
                               int channels, int num_levels, int num_query, int n_curr_points,
-                              int n_temporal_points, int t_window, int dtype, void *stream)
+                              int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
+                              void *stream)
 {
     FusedArgs a{};
     int rc = fill_fused(a, value, spatial_shapes_host, level_start_index_host, frame_table_host, ref, off_curr,
                         logit_curr, off_temporal, logit_temporal, query_order, num_frames, spatial_size, num_heads,
-                        channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, dtype);
+                        channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, ref_dim,
+                        temporal_ref_mode, dtype);
     if (rc) return rc;
     if (num_frames == 0 || num_query == 0) return DEVIS_MSDA_OK;
     if (!output) return DEVIS_MSDA_ERR_NULL_POINTER;
     a.out = output;
+    a.loc_out[0] = reinterpret_cast<float *>(loc_curr_out);
+    a.aw_out[0] = reinterpret_cast<float *>(aw_curr_out);
+    a.loc_out[1] = a.n_seg > 1 ? reinterpret_cast<float *>(loc_temporal_out) : nullptr;
+    a.aw_out[1] = a.n_seg > 1 ? reinterpret_cast<float *>(aw_temporal_out) : nullptr;
     dim3 grid;
     int threads;
     size_t smem;
+    // the general (decoder) form: boxes, per-level / instance-aware temporal reference points, by-products
+    const bool general = ref_dim == 4 || (a.n_seg > 1 && temporal_ref_mode != 0) || loc_curr_out || aw_curr_out ||
+                         a.loc_out[1] || a.aw_out[1];
+    if (general) {
+        rc = fused_grid(a, 0, grid, threads, smem, 1);
+        if (rc) return rc;
+        if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd_kernel<true, 1, true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else tmsda_fused_fwd_kernel<false, 1, true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
+    }
     // bf16 value: four lanes x 8 channels per (query, head) like msda_fwd8_kernel (tuning key 4: 1 never, 2 always)
     const int wide_mode = g_tuning[4].load();
     if (wide_mode == 2 || (wide_mode == 0 && dtype == DEVIS_MSDA_BF16)) {
@@ -723,7 +706,7 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
         smem = (size_t)(a.n_slots[0] + a.n_slots[1]) * sizeof(int4) + (size_t)(threads / 32) * Tap16::kBytesPerWarp;
         if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd8_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
         else tmsda_fused_fwd8_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        return check_launch();
+        return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
     }
     // two queries per lane group for fp32 at encoder sizes, like msda_fwdc_kernel (tuning key 1 overrides)
     int qpg = g_tuning[1].load();
@@ -737,7 +720,7 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
         if (qpg == 2) tmsda_fused_fwd_kernel<false, 2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
         else tmsda_fused_fwd_kernel<false, 1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     }
-    return check_launch();
+    return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
 }
 
 int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_host,
@@ -745,15 +728,17 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
                                const void *ref, const void *off_curr, const void *logit_curr,
                                const void *off_temporal, const void *logit_temporal, const void *grad_output,
                                void *grad_value, void *grad_off_curr, void *grad_logit_curr,
-                               void *grad_off_temporal, void *grad_logit_temporal, const int32_t *query_order,
-                               int num_frames, int spatial_size, int num_heads, int channels, int num_levels,
-                               int num_query, int n_curr_points, int n_temporal_points, int t_window, int dtype,
+                               void *grad_off_temporal, void *grad_logit_temporal, void *grad_ref,
+                               const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
+                               int channels, int num_levels, int num_query, int n_curr_points,
+                               int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
                                unsigned flags, void *stream)
 {
     FusedArgs a{};
     int rc = fill_fused(a, value, spatial_shapes_host, level_start_index_host, frame_table_host, ref, off_curr,
                         logit_curr, off_temporal, logit_temporal, query_order, num_frames, spatial_size, num_heads,
-                        channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, dtype);
+                        channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, ref_dim,
+                        temporal_ref_mode, dtype);
     if (rc) return rc;
     if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
@@ -768,6 +753,13 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
             if (e != cudaSuccess) return cuda_fail(e);
         }
     }
+    if (grad_ref) {
+        const size_t bytes = (size_t)num_frames * num_query * num_levels * ref_dim * sizeof(float);
+        if (bytes) {
+            const cudaError_t e = cudaMemsetAsync(grad_ref, 0, bytes, st);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+    }
     if (num_frames == 0 || num_query == 0) return DEVIS_MSDA_OK;
     if (!grad_output || !grad_off_curr || !grad_logit_curr || (a.n_seg > 1 && (!grad_off_temporal || !grad_logit_temporal)))
         return DEVIS_MSDA_ERR_NULL_POINTER;
@@ -777,6 +769,7 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
     a.grad_logit[0] = reinterpret_cast<float *>(grad_logit_curr);
     a.grad_off[1] = reinterpret_cast<float *>(grad_off_temporal);
     a.grad_logit[1] = reinterpret_cast<float *>(grad_logit_temporal);
+    a.grad_ref = reinterpret_cast<float *>(grad_ref);
     dim3 grid;
     int threads;
     size_t smem;
@@ -791,10 +784,17 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
             smem += park;
         }
     }
-    if (half_acc) tmsda_fused_bwd_kernel<true, true><<<grid, threads, smem, st>>>(a);
-    else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
-    else tmsda_fused_bwd_kernel<false><<<grid, threads, smem, st>>>(a);
-    return check_launch();
+    const bool general = ref_dim == 4 || (a.n_seg > 1 && temporal_ref_mode != 0) || grad_ref;
+    if (general) {
+        if (half_acc) tmsda_fused_bwd_kernel<true, true, true><<<grid, threads, smem, st>>>(a);
+        else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true, false, true><<<grid, threads, smem, st>>>(a);
+        else tmsda_fused_bwd_kernel<false, false, true><<<grid, threads, smem, st>>>(a);
+    } else {
+        if (half_acc) tmsda_fused_bwd_kernel<true, true><<<grid, threads, smem, st>>>(a);
+        else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true><<<grid, threads, smem, st>>>(a);
+        else tmsda_fused_bwd_kernel<false><<<grid, threads, smem, st>>>(a);
+    }
+    return check_launch(DEVIS_MSDA_KERNEL_FUSED_BWD);
 }
 
 }  // extern "C"

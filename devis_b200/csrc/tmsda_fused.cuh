@@ -12,7 +12,14 @@
 //     loc = ref[level 0] + off / (W_level, H_level)      (temporal taps start from the level-0 point, :447)
 //     w   = exp(logit - rowmax) / rowsum                 (rowmax, rowsum over all K taps of the (query, head))
 // The backward returns d/d(off) = grad_loc / (W, H) and d/d(logit) = w * (grad_w - sum_k w_k grad_w_k) directly.
-// Encoder form only (2-d reference points); the decoder's taps are 1000x fewer and keep the unfused path.
+// Template GEN = false is that encoder form and nothing else (its hot loop pays for no generality).  GEN = true adds what
+// the DECODER's prologue needs (ms_deform_attn.py:320-404), where the taps are 1000x fewer and the point is to replace
+// ~100 small elementwise launches per layer, not bytes:
+//     box reference points (ref_dim 4):  loc = ref.xy + ((off / P) * ref.wh) * 0.5                        (:369-371, :390-394)
+//     temporal taps start from the level's own point of the query's frame (tref_mode 1, :346-347) or, instance aware,
+//     from the SAME query's point in the sampled frame (tref_mode 2, :342-344)
+//     the sampling locations and softmax weights are written out as by-products (the module's 5-tuple, :414)
+//     d/d(ref) is accumulated (float atomics on a (T, Lq, L, ref_dim) tensor; decoder layer 0 learns its reference points)
 // Work split, tap exchange, reductions: identical to msda_fwd.cuh / msda_bwd.cuh (LPG = 8, D = 32).
 #pragma once
 #include "msda_bwd.cuh"
@@ -23,7 +30,14 @@ namespace devis {
 
 struct FusedArgs {
     const void *value;
-    const float *ref;          // (T, Lq, L, 2)
+    const float *ref;          // (T, Lq, L, ref_dim)
+    int ref_dim;               // 2: points (x, y); 4: boxes (x, y, w, h)                                  [GEN]
+    int tref_mode;             // reference point of a temporal tap: 0 level 0 of the query's frame (encoder),
+                               // 1 the tap's level, query's frame; 2 the tap's level, sampled frame      [GEN]
+    float inv_p[2];            // box form: 1 / points per slot (torch divides by a scalar as x * (1/s))   [GEN]
+    float *loc_out[2];         // optional by-products of the forward, laid out like the unfused operands  [GEN]
+    float *aw_out[2];
+    float *grad_ref;           // backward, optional: (T, Lq, L, ref_dim), zero-filled by the caller       [GEN]
     const float *off[2];       // raw sampling offsets, current / temporal
     const float *logit[2];     // raw attention logits, current / temporal
     int n_slots[2];
@@ -100,38 +114,75 @@ __device__ __forceinline__ void row_softmax_stats(const FusedArgs &a, size_t row
 // raw operands of one tap as the Linear layers wrote them; loaded one exchange AHEAD of their use (like
 // msda_fwdc_kernel's load_taps) so that their DRAM latency hides under the 32 corner gathers of the exchange before
 struct RawTap {
-    float2 off;   // sampling offset (pixels of the tap's level)
-    float2 rf;    // reference point the tap starts from
+    float2 off;   // sampling offset (pixels of the tap's level; box form: in units of box size / (2 P))
+    float4 rf;    // reference point (x, y) or box (x, y, w, h) the tap starts from
     float lg;     // attention logit
+    int ref_row;  // GEN: row of `ref` / `grad_ref` this tap reads (in units of ref_dim floats)
 };
 
+template <bool GEN = false>
 __device__ __forceinline__ RawTap load_raw_tap(const FusedArgs &a, int sg, size_t row, size_t qrow, int k, bool live)
 {
     RawTap r;
     r.off = make_float2(0.f, 0.f);
-    r.rf = make_float2(0.f, 0.f);
+    r.rf = make_float4(0.f, 0.f, 0.f, 0.f);
     r.lg = 0.f;
+    r.ref_row = 0;
     const int P = a.P[sg], K = a.n_slots[sg] * P;
     if (live && k < K) {
-        const int level = mod_l(div_p(k, P, pow2_shift(P)), a.src.L, pow2_shift(a.src.L));
+        const int slot = div_p(k, P, pow2_shift(P));
+        const int level = mod_l(slot, a.src.L, pow2_shift(a.src.L));
         r.off = ld_stream_f2(reinterpret_cast<const float2 *>(a.off[sg] + row * K * 2) + k);
-        r.rf = __ldg(reinterpret_cast<const float2 *>(a.ref + (qrow * a.src.L + (sg == 0 ? level : 0)) * 2));
+        if (!GEN) {
+            const float2 p = __ldg(reinterpret_cast<const float2 *>(a.ref + (qrow * a.src.L + (sg == 0 ? level : 0)) * 2));
+            r.rf.x = p.x;
+            r.rf.y = p.y;
+        } else {
+            size_t rrow = qrow;
+            int lvl = level;
+            if (sg == 1) {
+                if (a.tref_mode == 0) {
+                    lvl = 0;
+                } else if (a.tref_mode == 2) {
+                    const int outer = (int)(qrow / (size_t)a.d.Lq);
+                    const int frame = a.src.frame[outer * a.src.Wt + slot / a.src.L];
+                    rrow = (size_t)((long long)qrow + (long long)(frame - outer) * a.d.Lq);
+                }
+            }
+            r.ref_row = (int)(rrow * a.src.L + lvl);
+            const float *rp = a.ref + (size_t)r.ref_row * a.ref_dim;
+            const float2 p = __ldg(reinterpret_cast<const float2 *>(rp));
+            r.rf.x = p.x;
+            r.rf.y = p.y;
+            if (a.ref_dim == 4) {
+                const float2 wh = __ldg(reinterpret_cast<const float2 *>(rp + 2));
+                r.rf.z = wh.x;
+                r.rf.w = wh.y;
+            }
+        }
         r.lg = __ldg(a.logit[sg] + row * K + k);      // in L1 since row_softmax_stats
     }
     return r;
 }
 
 // the fused prologue on prefetched operands:  loc = ref + off / (W, H)  with torch's own rounding (IEEE division, then
-// addition),  w = exp(logit - rowmax) / rowsum
-__device__ __forceinline__ void raw_to_operands(const RawTap &r, const int4 sl, float rmax, float rinv, float &x, float &y,
-                                                float &w)
+// addition),  w = exp(logit - rowmax) / rowsum;  box form (GEN, ref_dim 4): loc = ref.xy + ((off * (1/P)) * ref.wh) * 0.5,
+// every product rounded separately, in torch's left-to-right order (ms_deform_attn.py:369-371)
+template <bool GEN = false>
+__device__ __forceinline__ void raw_to_operands(const FusedArgs &a, int sg, const RawTap &r, const int4 sl, float rmax,
+                                                float rinv, float &x, float &y, float &w)
 {
-    x = __fadd_rn(r.rf.x, __fdiv_rn(r.off.x, (float)sl.y));
-    y = __fadd_rn(r.rf.y, __fdiv_rn(r.off.y, (float)sl.x));
+    if (GEN && a.ref_dim == 4) {
+        x = __fadd_rn(r.rf.x, __fmul_rn(__fmul_rn(__fmul_rn(r.off.x, a.inv_p[sg]), r.rf.z), 0.5f));
+        y = __fadd_rn(r.rf.y, __fmul_rn(__fmul_rn(__fmul_rn(r.off.y, a.inv_p[sg]), r.rf.w), 0.5f));
+    } else {
+        x = __fadd_rn(r.rf.x, __fdiv_rn(r.off.x, (float)sl.y));
+        y = __fadd_rn(r.rf.y, __fdiv_rn(r.off.y, (float)sl.x));
+    }
     w = expf(r.lg - rmax) * rinv;
 }
 
-template <bool BF16, int QPG>
+template <bool BF16, int QPG, bool GEN = false>
 __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
@@ -169,7 +220,7 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
 
     RawTap nxt[QPG];
 #pragma unroll
-    for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, 0, row[i], qrow[i], j, qlive[i]);
+    for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap<GEN>(a, 0, row[i], qrow[i], j, qlive[i]);
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.P[sg], K = a.n_slots[sg] * P, pshift = pow2_shift(P);   // P % 4 == 0 (checked by the launcher)
@@ -186,16 +237,20 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
             for (int i = 0; i < QPG; ++i) cur[i] = nxt[i];
             if (k0 + LPG < K) {
 #pragma unroll
-                for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, sg, row[i], qrow[i], k + LPG, qlive[i]);
+                for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap<GEN>(a, sg, row[i], qrow[i], k + LPG, qlive[i]);
             } else if (sg + 1 < a.n_seg) {
 #pragma unroll
-                for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap(a, sg + 1, row[i], qrow[i], j, qlive[i]);
+                for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap<GEN>(a, sg + 1, row[i], qrow[i], j, qlive[i]);
             }
 #pragma unroll
             for (int i = 0; i < QPG; ++i) {
                 const bool live = klive && qlive[i];
                 float x = 0.f, y = 0.f, w = 0.f;
-                if (live) raw_to_operands(cur[i], sl, rmax[i], rinv[i], x, y, w);
+                if (live) raw_to_operands<GEN>(a, sg, cur[i], sl, rmax[i], rinv[i], x, y, w);
+                if (GEN && live) {      // the decoder module's 5-tuple: locations and weights as the unfused path lays them out
+                    if (a.loc_out[sg]) reinterpret_cast<float2 *>(a.loc_out[sg] + row[i] * K * 2)[k] = make_float2(x, y);
+                    if (a.aw_out[sg]) a.aw_out[sg][row[i] * K + k] = w;
+                }
                 const TapGeom t = tap_geometry(x, y, sl, live);
                 float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
                 parity ^= 1;
@@ -256,9 +311,9 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
             const unsigned pitch = (unsigned)sl.y * rowbytes;
             // loaded at use: with 8 groups per warp a prefetch one exchange ahead does not pay here (531 vs 524 us; the
             // same holds for msda_fwd8_kernel, 431 vs 403 us)
-            const RawTap cur = load_raw_tap(a, sg, row, qrow, k, qlive);
+            const RawTap cur = load_raw_tap<false>(a, sg, row, qrow, k, qlive);
             float x = 0.f, y = 0.f, w = 0.f;
-            if (qlive) raw_to_operands(cur, sl, rmax, rinv, x, y, w);
+            if (qlive) raw_to_operands<false>(a, sg, cur, sl, rmax, rinv, x, y, w);
             const TapGeom t = tap_geometry(x, y, sl, qlive);
             float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
             parity ^= 1;
@@ -282,7 +337,7 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
 }
 
 // HALF_ACC: bf16 grad_value with packed bf16 reductions (see msda_bwd_kernel)
-template <bool BF16, bool HALF_ACC = false>
+template <bool BF16, bool HALF_ACC = false, bool GEN = false>
 __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
@@ -325,7 +380,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
 
     float dotp = 0.f;   // this lane's share of sum_k w_k * d(out.grad_out)/d(w_k)
     int slot_base = 0, parity = 0, it = 0;
-    RawTap nxt = load_raw_tap(a, 0, row, qrow, j, qlive);
+    RawTap nxt = load_raw_tap<GEN>(a, 0, row, qrow, j, qlive);
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int P = a.P[sg], K = a.n_slots[sg] * P, pshift = pow2_shift(P);
         float *goff = a.grad_off[sg] + row * K * 2;
@@ -336,10 +391,10 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
             const int ls = live ? div_p(k, P, pshift) : 0;
             const int4 sl = s_slot[slot_base + ls];
             const RawTap cur = nxt;
-            if (k0 + LPG < K) nxt = load_raw_tap(a, sg, row, qrow, k + LPG, qlive);
-            else if (sg + 1 < a.n_seg) nxt = load_raw_tap(a, sg + 1, row, qrow, j, qlive);
+            if (k0 + LPG < K) nxt = load_raw_tap<GEN>(a, sg, row, qrow, k + LPG, qlive);
+            else if (sg + 1 < a.n_seg) nxt = load_raw_tap<GEN>(a, sg + 1, row, qrow, j, qlive);
             float x = 0.f, y = 0.f, w = 0.f;
-            if (live) raw_to_operands(cur, sl, rmax, rinv, x, y, w);
+            if (live) raw_to_operands<GEN>(a, sg, cur, sl, rmax, rinv, x, y, w);
             const TapGeom t = tap_geometry(x, y, sl, live);
             float *buf = xbuf + parity * X::kWordsPerWarpBuf;
             parity ^= 1;
@@ -377,6 +432,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
             }
             float A[4];
             reduce_scatter_taps<LPG>(dsum, j, A);
+            float gr[4] = {0.f, 0.f, 0.f, 0.f};   // GEN: this tap's d/d(ref x, y, w, h)
             if (live) {
                 const bool hit = t.ok != 0u;
                 const float hh = (t.ok & 1u) ? t.hh : 0.f, lh = (t.ok & 2u) ? t.lh : 0.f;
@@ -388,10 +444,45 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
                 const float gy = hw * (b_in * A[2] - t_in * A[0]) + lw * (b_in * A[3] - t_in * A[1]);
                 // d/d(loc) = (W gx w, H gy w) as in msda_bwd.cuh, then the chain rule of loc = ref + off / (W, H): the two
                 // factors cancel (the reference's multiply-then-divide sequence differs from this by <= 1 ulp)
-                st_stream_f2(reinterpret_cast<float2 *>(goff) + k, hit ? make_float2(gx * w, gy * w) : make_float2(0.f, 0.f));
+                if (!GEN) {
+                    st_stream_f2(reinterpret_cast<float2 *>(goff) + k, hit ? make_float2(gx * w, gy * w) : make_float2(0.f, 0.f));
+                } else {
+                    // d/d(loc) in normalised coordinates, as msda_bwd.cuh writes it; then the chain rule of the prologue
+                    const float glx = hit ? (float)sl.y * gx * w : 0.f, gly = hit ? (float)sl.x * gy * w : 0.f;
+                    float2 go2;
+                    if (a.ref_dim == 4) {
+                        const float sx = a.inv_p[sg] * 0.5f;
+                        go2 = make_float2(glx * (sx * cur.rf.z), gly * (sx * cur.rf.w));
+                        gr[2] = glx * (cur.off.x * sx);
+                        gr[3] = gly * (cur.off.y * sx);
+                    } else {
+                        go2 = hit ? make_float2(gx * w, gy * w) : make_float2(0.f, 0.f);
+                    }
+                    gr[0] = glx;
+                    gr[1] = gly;
+                    st_stream_f2(reinterpret_cast<float2 *>(goff) + k, go2);
+                }
                 if (park) s_park[it * blockDim.x] = make_float2(w, val);
                 else glog[k] = val;       // parked; finished below once the row's  sum_k w_k val_k  is known
                 dotp = fmaf(w, val, dotp);
+            }
+            if (GEN && a.grad_ref) {
+                // the 4 taps an aligned lane quad prepared belong to one slot (P % 4 == 0), hence to one reference point:
+                // sum them in the quad, one atomic per component
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    gr[c] += __shfl_xor_sync(0xffffffffu, gr[c], 1, 4);
+                    gr[c] += __shfl_xor_sync(0xffffffffu, gr[c], 2, 4);
+                }
+                if (live && (j & 3) == 0) {
+                    float *gp = a.grad_ref + (size_t)cur.ref_row * a.ref_dim;
+                    atomicAdd(gp, gr[0]);
+                    atomicAdd(gp + 1, gr[1]);
+                    if (a.ref_dim == 4) {
+                        atomicAdd(gp + 2, gr[2]);
+                        atomicAdd(gp + 3, gr[3]);
+                    }
+                }
             }
             ++it;
         }

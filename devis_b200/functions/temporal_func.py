@@ -120,25 +120,37 @@ class TemporalMSDeformAttnFunction(Function):
 
 
 class TemporalMSDeformAttnFusedFunction(Function):
-    """apply(value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None) -> (T, Lq, M*D)
+    """apply(value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None,
+             temporal_ref_mode=TREF_LEVEL0, want_sampling=False) -> out (T, Lq, M*D)
+                                                           | (out, loc_curr, aw_curr, loc_temporal, aw_temporal)
 
-    Whole-clip temporal attention straight from the Linear outputs (encoder form): the joint softmax over all taps
-    and ``ref + off / (W, H)`` (ms_deform_attn.py:240-260, 437-452) happen inside the kernels, and the backward returns
-    the gradients of the raw offsets and logits.  value (T,S,M,32) fp32|bf16; ref (T,Lq,L,2); off_curr
-    (T,Lq,M,L,Pc,2); logit_curr (T,Lq,M,L*Pc); off_temporal (T,Lq,M,Wt*L,Pt,2); logit_temporal (T,Lq,M,Wt*L*Pt)."""
+    Whole-clip temporal attention straight from the Linear outputs: the joint softmax over all taps and the sampling
+    location arithmetic (encoder: ms_deform_attn.py:240-260, 437-452; decoder: :320-404, points or boxes, instance
+    aware or not) happen inside the kernels, and the backward returns the gradients of the raw offsets and logits (and of
+    the reference points when they require grad).  value (T,S,M,32) fp32|bf16; ref (T,Lq,L,2|4); off_curr
+    (T,Lq,M,L,Pc,2); logit_curr (T,Lq,M,L*Pc); off_temporal (T,Lq,M,Wt*L,Pt,2); logit_temporal (T,Lq,M,Wt*L*Pt).
+    temporal_ref_mode: _lib.TREF_LEVEL0 (encoder) | TREF_OWN | TREF_SAMPLED (decoder, instance aware).
+    want_sampling: also return the sampling locations and softmax weights the kernel computed (non-differentiable
+    by-products: what TemporalMSDeformAttnDecoder.forward hands to visualize_att_maps.py)."""
 
     @staticmethod
-    def supported(like, head_dim, reference_points, n_curr_points=4, n_temporal_points=4):
-        """`like`: a tensor with value's device, dtype and element count (e.g. the module's input_flatten)"""
-        return (like.is_cuda and like.dtype in (torch.float32, torch.bfloat16) and head_dim == 32
+    def supported(value, reference_points, n_curr_points=4, n_temporal_points=4):
+        """`value`: the projected value tensor (T,S,M,D) (or any tensor with its device, dtype and shape)"""
+        return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16) and value.shape[-1] == 32
                 and n_curr_points % 4 == 0 and n_temporal_points % 4 == 0
-                and reference_points.shape[-1] == 2 and like.numel() * like.element_size() < (1 << 32)
-                and not MSDA.deterministic_enabled(like.dtype))
+                and reference_points.shape[-1] in (2, 4) and value.numel() * value.element_size() < (1 << 32)
+                and not MSDA.deterministic_enabled(value.dtype))
 
     @staticmethod
-    def forward(ctx, value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None):
+    def forward(ctx, value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None,
+                temporal_ref_mode=_lib.TREF_LEVEL0, want_sampling=False):
+        if not value.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")
+        if value.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f'"temporal_ms_deform_attn_fused" not implemented for \'{value.dtype}\'')
         f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
         value = value if value.is_contiguous() else value.contiguous()
+        ref_in_dtype = ref.dtype
         ref, oc, lc = f32(ref), f32(off_curr), f32(logit_curr)
         has_t = geometry.t_window > 0 and off_temporal is not None
         ot = f32(off_temporal) if has_t else None
@@ -146,48 +158,69 @@ class TemporalMSDeformAttnFusedFunction(Function):
         t, s, m, d = value.shape
         lq, pc = oc.shape[1], oc.shape[4]
         pt = ot.shape[4] if has_t else 0
+        ref_dim = ref.shape[-1]
         if t != geometry.n_frames or s != geometry.spatial_size or oc.shape[3] != geometry.n_levels:
             raise RuntimeError("operands do not match the clip geometry")
+        if tuple(ref.shape) != (t, lq, geometry.n_levels, ref_dim) or ref_dim not in (2, 4):
+            raise RuntimeError(f"reference points {tuple(ref.shape)} must be (T, Lq, L, 2|4)")
         out = torch.empty((t, lq, m * d), dtype=value.dtype, device=value.device)
+        samp = [None] * 4
+        if want_sampling:
+            samp[0], samp[1] = torch.empty_like(oc), torch.empty((t, lq, m, geometry.n_levels, pc), dtype=torch.float32,
+                                                                 device=value.device)
+            if has_t:
+                samp[2] = torch.empty_like(ot)
+                samp[3] = torch.empty((t, lq, m, geometry.t_window * geometry.n_levels, pt), dtype=torch.float32,
+                                      device=value.device)
         with torch.cuda.device(value.device):
             _lib.check(_lib.load().devis_tmsda_fused_forward(
                 _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr, _ptr(ref), _ptr(oc), _ptr(lc),
-                _ptr(ot), _ptr(lt), _ptr(out), _ptr(query_order), t, s, m, d, geometry.n_levels, lq, pc, pt,
-                geometry.t_window if has_t else 0, _DTYPES[value.dtype], torch.cuda.current_stream().cuda_stream))
-        ctx.geometry, ctx.has_t = geometry, has_t
-        ctx.dims = (t, s, m, d, lq, pc, pt)
+                _ptr(ot), _ptr(lt), _ptr(out), _ptr(samp[0]), _ptr(samp[1]), _ptr(samp[2]), _ptr(samp[3]),
+                _ptr(query_order), t, s, m, d, geometry.n_levels, lq, pc, pt,
+                geometry.t_window if has_t else 0, ref_dim, int(temporal_ref_mode), _DTYPES[value.dtype],
+                torch.cuda.current_stream().cuda_stream))
+        ctx.geometry, ctx.has_t, ctx.tref = geometry, has_t, int(temporal_ref_mode)
+        ctx.dims = (t, s, m, d, lq, pc, pt, ref_dim)
         ctx.in_dtypes = (off_curr.dtype, logit_curr.dtype, off_temporal.dtype if has_t else None,
-                         logit_temporal.dtype if has_t else None)
+                         logit_temporal.dtype if has_t else None, ref_in_dtype)
         ctx.save_for_backward(value, ref, oc, lc, ot, lt, query_order)
-        return out
+        if not want_sampling:
+            return out
+        extras = tuple(x for x in samp if x is not None)
+        ctx.mark_non_differentiable(*extras)
+        ctx.n_extras = len(extras)
+        return (out,) + extras
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, grad_output):
+    def backward(ctx, grad_output, *_unused):
         value, ref, oc, lc, ot, lt, query_order = ctx.saved_tensors
         geometry, has_t = ctx.geometry, ctx.has_t
-        t, s, m, d, lq, pc, pt = ctx.dims
+        t, s, m, d, lq, pc, pt, ref_dim = ctx.dims
         gout = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
         gout = gout if gout.is_contiguous() else gout.contiguous()
         need_gv = ctx.needs_input_grad[0]
+        need_gref = ctx.needs_input_grad[1]
         half_acc = need_gv and MSDA.bf16_accumulate_enabled(value)
         gv = torch.empty(value.shape, dtype=value.dtype if half_acc else torch.float32, device=value.device) \
             if need_gv else None
         goc, glc = torch.empty_like(oc), torch.empty_like(lc)
         got = torch.empty_like(ot) if has_t else None
         glt = torch.empty_like(lt) if has_t else None
+        gref = torch.empty_like(ref) if need_gref else None
         with torch.cuda.device(value.device):
             _lib.check(_lib.load().devis_tmsda_fused_backward(
                 _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr, _ptr(ref), _ptr(oc), _ptr(lc),
-                _ptr(ot), _ptr(lt), _ptr(gout), _ptr(gv), _ptr(goc), _ptr(glc), _ptr(got), _ptr(glt), _ptr(query_order),
-                t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0, _DTYPES[value.dtype],
+                _ptr(ot), _ptr(lt), _ptr(gout), _ptr(gv), _ptr(goc), _ptr(glc), _ptr(got), _ptr(glt), _ptr(gref),
+                _ptr(query_order), t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0,
+                ref_dim, ctx.tref, _DTYPES[value.dtype],
                 (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE) | (_lib.FLAG_BF16_GRAD_VALUE if half_acc else 0),
                 torch.cuda.current_stream().cuda_stream))
-        doc, dlc, dot, dlt = ctx.in_dtypes
+        doc, dlc, dot, dlt, dref = ctx.in_dtypes
         if gv is not None and gv.dtype != value.dtype:
             gv = gv.to(value.dtype)
         cast = lambda g, dt: g if (g is None or g.dtype == dt) else g.to(dt)
-        return gv, None, cast(goc, doc), cast(glc, dlc), cast(got, dot), cast(glt, dlt), None, None
+        return gv, cast(gref, dref), cast(goc, doc), cast(glc, dlc), cast(got, dot), cast(glt, dlt), None, None, None, None
 
 
 def temporal_ms_deform_attn(value, loc_curr, aw_curr, loc_temporal, aw_temporal, geometry, query_order=None):

@@ -9,9 +9,9 @@
 
 What differs from the reference is only HOW the temporal modules evaluate a clip: the reference loops
 over the T frames in Python and issues two op calls and one gather copy of ``value`` per frame; here
-the whole clip is one ``TemporalMSDeformAttnFunction`` call that reads ``value`` in place, and in the
-encoder (``fuse_prologue``) the kernels also take over the joint softmax and the location arithmetic
-(``TemporalMSDeformAttnFusedFunction``), reading the Linear outputs directly.
+the whole clip is one ``TemporalMSDeformAttnFunction`` call that reads ``value`` in place, and with
+``fuse_prologue`` (default, encoder and decoder) the kernels also take over the joint softmax and the location
+arithmetic (``TemporalMSDeformAttnFusedFunction``), reading the Linear outputs directly.
 """
 import math
 import warnings
@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from .. import clip_geometry
+from .. import _lib, clip_geometry
 from ..functions import MSDeformAttnFunction, TemporalMSDeformAttnFusedFunction, temporal_ms_deform_attn
 
 
@@ -127,7 +127,7 @@ class TemporalMSDeformAttnBase(nn.Module):
         self.output_proj = nn.Linear(d_model, d_model)
         # encoder only: walk the pixel-grid queries in 2-D tiles (cache locality, see ClipGeometry.tile_order)
         self.query_tile = (8, 8)
-        # encoder only: let the kernels read the raw Linear outputs (joint softmax and `ref + off / (W, H)` fused in)
+        # let the kernels read the raw Linear outputs (joint softmax and the sampling-location arithmetic fused in)
         self.fuse_prologue = True
         self._reset_parameters()
 
@@ -152,9 +152,10 @@ class TemporalMSDeformAttnBase(nn.Module):
         halves of ONE softmax over all L*Pc + Wt*L*Pt taps.  (No padding-mask fill: the temporal
         modules never receive a mask, devis_transformer.py:120.)"""
         t, lq, _ = query.shape
-        s = input_flatten.shape[1]
         m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
-        value = self.value_proj(input_flatten).view(t, s, m, self.d_model // m)
+        value = None
+        if input_flatten is not None:     # None: the caller has projected value already
+            value = self.value_proj(input_flatten).view(t, input_flatten.shape[1], m, self.d_model // m)
         off_t = self.temporal_sampling_offsets(query).view(t, lq, m, wt * nl, pt, 2)
         off_c = self.sampling_offsets(query).view(t, lq, m, nl, pc, 2)
         logits = torch.cat([self.attention_weights(query).view(t, lq, m, nl * pc),
@@ -187,12 +188,11 @@ class TemporalMSDeformAttnEncoder(TemporalMSDeformAttnBase):
         if self.query_tile and query.shape[1] == geom.spatial_size:
             order = geom.tile_order(query.device, *self.query_tile)
 
-        if self.fuse_prologue and TemporalMSDeformAttnFusedFunction.supported(
-                input_flatten, self.d_model // self.n_heads, reference_points, self.n_curr_points,
-                self.n_temporal_points):
-            t, lq, _ = query.shape
-            m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
-            value = self.value_proj(input_flatten).view(t, input_flatten.shape[1], m, self.d_model // m)
+        t, lq, _ = query.shape
+        m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
+        value = self.value_proj(input_flatten).view(t, input_flatten.shape[1], m, self.d_model // m)
+        # decided on the PROJECTED value (under autocast it is half precision while input_flatten is not)
+        if self.fuse_prologue and TemporalMSDeformAttnFusedFunction.supported(value, reference_points, pc, pt):
             out = TemporalMSDeformAttnFusedFunction.apply(
                 value, reference_points,
                 self.sampling_offsets(query).view(t, lq, m, nl, pc, 2),
@@ -201,7 +201,7 @@ class TemporalMSDeformAttnEncoder(TemporalMSDeformAttnBase):
                 self.temporal_attention_weights(query).view(t, lq, m, wt * nl * pt), geom, order)
             return self.output_proj(out), None
 
-        value, off_c, off_t, aw_c, aw_t = self._compute_deformable_attention(query, input_flatten)
+        _, off_c, off_t, aw_c, aw_t = self._compute_deformable_attention(query, None)
 
         wh = _wh(cur_shapes, off_c.dtype)
         loc_c = reference_points[:, :, None, :, None, :] + off_c / wh[None, None, None, :, None, :]
@@ -232,7 +232,27 @@ class TemporalMSDeformAttnDecoder(TemporalMSDeformAttnBase):
         if reference_points.shape[0] != n_frames:
             reference_points = reference_points.reshape((n_frames, q) + tuple(reference_points.shape[-2:]))
         geom = self._geometry(n_frames, input_spatial_shapes, input_level_start_index, temporal_offsets)
-        value, off_c, off_t, aw_c, aw_t = self._compute_deformable_attention(query, input_flatten)
+        m, nl, wt, pc, pt = self.n_heads, self.n_levels, self.t_window, self.n_curr_points, self.n_temporal_points
+        value = self.value_proj(input_flatten).view(n_frames, input_flatten.shape[1], m, self.d_model // m)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
+                reference_points.shape[-1]))
+
+        if self.fuse_prologue and TemporalMSDeformAttnFusedFunction.supported(value, reference_points, pc, pt):
+            # one launch each way: softmax, `ref + off / (W, H)` or the box form, the instance-aware reference lookup and
+            # the 5-tuple's locations / weights (by-products, not differentiable) all happen in the kernels
+            out, loc_c, aw_c, loc_t, aw_t = TemporalMSDeformAttnFusedFunction.apply(
+                value, reference_points,
+                self.sampling_offsets(query).view(n_frames, q, m, nl, pc, 2),
+                self.attention_weights(query).view(n_frames, q, m, nl * pc),
+                self.temporal_sampling_offsets(query).view(n_frames, q, m, wt * nl, pt, 2),
+                self.temporal_attention_weights(query).view(n_frames, q, m, wt * nl * pt), geom, None,
+                _lib.TREF_SAMPLED if self.dec_instance_aware_att else _lib.TREF_OWN, True)
+            out = self.output_proj(out.flatten(0, 1)[None])
+            return (out, [loc_c[t][None] for t in range(n_frames)], [loc_t[t][None] for t in range(n_frames)],
+                    aw_c, aw_t)
+
+        _, off_c, off_t, aw_c, aw_t = self._compute_deformable_attention(query, None)
 
         # reference point each temporal (slot, level) starts from: the same query's own reference in the
         # sampled frame when instance-aware (:342-344), else its frame-t reference repeated (:346-347)
@@ -246,13 +266,10 @@ class TemporalMSDeformAttnDecoder(TemporalMSDeformAttnBase):
             wh = _wh(cur_shapes, off_c.dtype)
             loc_c = reference_points[:, :, None, :, None, :] + off_c / wh[None, None, None, :, None, :]
             loc_t = ref_t[:, :, None, :, None, :] + off_t / wh.repeat(self.t_window, 1)[None, None, None, :, None, :]
-        elif reference_points.shape[-1] == 4:
+        else:
             loc_c = reference_points[:, :, None, :, None, :2] \
                 + (off_c / self.n_curr_points) * reference_points[:, :, None, :, None, 2:] * 0.5
             loc_t = ref_t[:, :, None, :, None, :2] + (off_t / self.n_temporal_points) * ref_t[:, :, None, :, None, 2:] * 0.5
-        else:
-            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
-                reference_points.shape[-1]))
 
         out = temporal_ms_deform_attn(value, loc_c, aw_c, loc_t, aw_t, geom, None)
         out = self.output_proj(out.flatten(0, 1)[None])

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DEVIS_MSDA_ABI_VERSION 1
+#define DEVIS_MSDA_ABI_VERSION 2
 
 /* element types of value / output / grad_output */
 #define DEVIS_MSDA_F32 0  /* value, loc, weights, outputs and all gradients float            */
@@ -68,14 +68,28 @@ const char *devis_msda_error_string(int code);
 int devis_msda_last_cuda_error(void);
 /* number of kernels this library has launched in this process (all threads) */
 uint64_t devis_msda_launch_count(void);
-/* Launch-shape knobs for benchmarking (process-wide; 0 restores the built-in heuristic).
+/* the same count per kernel family: lets a caller (and the parity tests) verify WHICH kernel served a call -- e.g.
+ * that the fused-prologue kernels ran and the module did not silently take the unfused path */
+#define DEVIS_MSDA_KERNEL_FWD_GROUPED 0   /* msda_fwd / msda_fwdc / msda_fwd8 (D = 16 | 32 lane-group kernels) */
+#define DEVIS_MSDA_KERNEL_FWD_GENERIC 1   /* msda_fwd_generic (any D, fp64) */
+#define DEVIS_MSDA_KERNEL_BWD_GROUPED 2   /* msda_bwd */
+#define DEVIS_MSDA_KERNEL_BWD_GENERIC 3   /* msda_bwd_generic */
+#define DEVIS_MSDA_KERNEL_FUSED_FWD 4     /* tmsda_fused_fwd / tmsda_fused_fwd8 (prologue fused in) */
+#define DEVIS_MSDA_KERNEL_FUSED_BWD 5     /* tmsda_fused_bwd */
+#define DEVIS_MSDA_KERNEL_BWD_SORTED 6    /* msda_bwds (deterministic, encoder form) */
+#define DEVIS_MSDA_KERNEL_AUX 7           /* absmax / fixed-point finalize helpers */
+#define DEVIS_MSDA_KERNEL_DCN 8           /* include/devis_deform_conv.h kernels */
+#define DEVIS_MSDA_KERNEL_FAMILIES 9
+uint64_t devis_msda_kernel_launches(int family);
+/* Developer knobs of the benchmarks (launch shapes, kernel A/B selection).  They are inert in a product process:
+ * unless the process was started with the environment variable DEVIS_MSDA_TUNING=1 this returns
+ * DEVIS_MSDA_ERR_UNSUPPORTED and every key stays at 0 = built-in heuristic.
  * key 0: forward threads per block, 1: forward queries per lane group,
  * key 2: backward threads per block, 3: backward queries per lane group,
- * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always (A/B testing),
+ * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always,
  * key 5: 8-lane forward kernel with 16-byte tap records: 0 = fp32 only (default), 1 = always, 2 = never,
- * key 6: 2 = experimental windowed whole-clip backward (per-block shared-memory pre-aggregation of grad_value in
- *        32-bit fixed point; encoder form only), anything else = off (default),
- * key 7: its window margin in pixels (0 = 6), key 8: its shared-memory budget in 128-byte rows (0 = 384). */
+ * key 6: 1 = deterministic mode uses the direct 64-bit scatter instead of the sorted kernel,
+ * key 7: sorted kernel's window margin in pixels (0 = 6), key 9: its first level with a window + 1. */
 int devis_msda_set_tuning(int key, int value);
 
 /*
@@ -152,34 +166,51 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
                          size_t workspace_bytes, void *stream);
 
 /*
- * Whole-clip temporal attention with the prologue fused in (encoder form).  Replaces, besides the per-frame op calls,
- * the elementwise chain that turns the Linear outputs into op operands: the cat + joint softmax over all
- * K = L*Pc + Wt*L*Pt taps (modules/ms_deform_attn.py:240-260) and `ref + off / (W, H)` for current and temporal taps
- * (:437-439, :447-452; temporal taps start from the LEVEL-0 reference point).
- *   ref            (num_frames, num_query, num_levels, 2) float   reference points (x, y), no gradient
+ * Whole-clip temporal attention with the prologue fused in.  Replaces, besides the per-frame op calls, the elementwise
+ * chain that turns the Linear outputs into op operands: the cat + joint softmax over all K = L*Pc + Wt*L*Pt taps
+ * (modules/ms_deform_attn.py:240-260) and the sampling-location arithmetic of the encoder (:437-439, :447-452) and of
+ * the decoder (:320-404).
+ *   ref            (num_frames, num_query, num_levels, ref_dim) float   reference points (x, y) or boxes (x, y, w, h)
  *   off_curr       (num_frames, num_query, num_heads, num_levels, n_curr_points, 2) float      raw sampling_offsets output
  *   logit_curr     (num_frames, num_query, num_heads, num_levels*n_curr_points) float           raw attention_weights output
  *   off_temporal   (num_frames, num_query, num_heads, t_window*num_levels, n_temporal_points, 2) float
  *   logit_temporal (num_frames, num_query, num_heads, t_window*num_levels*n_temporal_points) float
- * value / output / grad_output: DEVIS_MSDA_F32 or DEVIS_MSDA_BF16; channels must be 32 and the point counts multiples of 4 (else DEVIS_MSDA_ERR_UNSUPPORTED
- * and the caller uses devis_tmsda_forward on materialised operands).  The backward writes d/d(off_*) and d/d(logit_*)
- * directly; grad_value (float) is zero-filled by the call; flags: DEVIS_MSDA_FLAG_NO_GRAD_VALUE only.
+ *   ref_dim 2:  loc = ref + off / (W_level, H_level)                    (:437-439 encoder, :327-330 decoder layer 0)
+ *   ref_dim 4:  loc = ref.xy + off / n_points * ref.wh * 0.5            (:369-371, :390-394 decoder with box refinement)
+ *   temporal_ref_mode   the reference point a TEMPORAL tap of (frame t, query q, level l, temporal slot j) starts from:
+ *       DEVIS_TMSDA_TREF_LEVEL0  ref[t][q][0]                       encoder (:447)
+ *       DEVIS_TMSDA_TREF_OWN     ref[t][q][l]                       decoder, dec_instance_aware_att off (:346-347)
+ *       DEVIS_TMSDA_TREF_SAMPLED ref[frame_table[t][j]][q][l]       decoder, instance aware (:342-344)
+ *   loc_*_out / aw_*_out   optional (NULL = skip): the sampling locations and softmax weights the kernel computed, laid
+ *       out like devis_tmsda_forward's operands -- what TemporalMSDeformAttnDecoder.forward returns next to its output
+ *       (:414, consumed by visualize_att_maps.py:162-165)
+ *   grad_ref       optional (NULL = skip): d/d(ref), like ref; zero-filled by the call, accumulated with float atomics
+ * value / output / grad_output: DEVIS_MSDA_F32 or DEVIS_MSDA_BF16; channels must be 32 and the point counts multiples of
+ * 4 (else DEVIS_MSDA_ERR_UNSUPPORTED and the caller uses devis_tmsda_forward on materialised operands).  The backward
+ * writes d/d(off_*) and d/d(logit_*) directly; grad_value (float) is zero-filled by the call; flags:
+ * DEVIS_MSDA_FLAG_NO_GRAD_VALUE, DEVIS_MSDA_FLAG_BF16_GRAD_VALUE (DETERMINISTIC -> DEVIS_MSDA_ERR_UNSUPPORTED).
  */
+#define DEVIS_TMSDA_TREF_LEVEL0 0
+#define DEVIS_TMSDA_TREF_OWN 1
+#define DEVIS_TMSDA_TREF_SAMPLED 2
 int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_host,
                               const int64_t *level_start_index_host, const int32_t *frame_table_host,
                               const void *ref, const void *off_curr, const void *logit_curr,
                               const void *off_temporal, const void *logit_temporal, void *output,
+                              void *loc_curr_out, void *aw_curr_out, void *loc_temporal_out, void *aw_temporal_out,
                               const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
                               int channels, int num_levels, int num_query, int n_curr_points,
-                              int n_temporal_points, int t_window, int dtype, void *stream);
+                              int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
+                              void *stream);
 int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_host,
                                const int64_t *level_start_index_host, const int32_t *frame_table_host,
                                const void *ref, const void *off_curr, const void *logit_curr,
                                const void *off_temporal, const void *logit_temporal, const void *grad_output,
                                void *grad_value, void *grad_off_curr, void *grad_logit_curr,
-                               void *grad_off_temporal, void *grad_logit_temporal, const int32_t *query_order,
-                               int num_frames, int spatial_size, int num_heads, int channels, int num_levels,
-                               int num_query, int n_curr_points, int n_temporal_points, int t_window, int dtype,
+                               void *grad_off_temporal, void *grad_logit_temporal, void *grad_ref,
+                               const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
+                               int channels, int num_levels, int num_query, int n_curr_points,
+                               int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
                                unsigned flags, void *stream);
 
 #ifdef __cplusplus

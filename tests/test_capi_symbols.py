@@ -81,7 +81,36 @@ def test_argument_validation_happens_before_any_cuda_call():
     before = lib.devis_msda_launch_count()
     assert lib.devis_msda_forward(null, null, null, null, null, null, 0, 4, 2, 32, 1, 0, 1, 64, 0, null) == 0
     assert lib.devis_msda_launch_count() == before
-    assert lib.devis_msda_set_tuning(99, 1) == -2 and lib.devis_msda_set_tuning(0, 0) == 0
+    assert lib.devis_msda_set_tuning(99, 1) == -2 and lib.devis_msda_set_tuning(0, 0) == 0   # conftest enables the knobs
+    # fused-prologue entry points: reference-point width and temporal reference mode are validated on the host
+    fused = lambda ref_dim, tref, d=32: lib.devis_tmsda_fused_forward(
+        *([null] * 15), 2, 8, 8, d, 1, 3, 4, 4, 1, ref_dim, tref, 0, null)
+    assert fused(3, 0) == -2 and fused(2, 3) == -2 and fused(2, 0, 16) == -8 and fused(4, 2) == -1
+    # per-family launch counters exist for every family the header names and nothing has been launched
+    header = open(HEADER).read()
+    n_fam = int(re.search(r"#define DEVIS_MSDA_KERNEL_FAMILIES (\d+)", header).group(1))
+    assert n_fam == 9 and all(lib.devis_msda_kernel_launches(f) == 0 for f in range(n_fam))
+    assert lib.devis_msda_kernel_launches(-1) == 0 and lib.devis_msda_kernel_launches(n_fam) == 0
+    for name in ("TREF_LEVEL0", "TREF_OWN", "TREF_SAMPLED"):
+        assert re.search(rf"#define DEVIS_TMSDA_{name} {getattr(_lib, name)}\b", header)
+    for name in re.findall(r"#define DEVIS_MSDA_(KERNEL_[A-Z_]+) (\d+)", header):
+        if name[0] != "KERNEL_FAMILIES":
+            assert getattr(_lib, name[0]) == int(name[1]), name
+
+
+def test_tuning_knobs_are_inert_in_a_product_process():
+    """devis_msda_set_tuning only works when the process was started with DEVIS_MSDA_TUNING=1 (developer benchmarks,
+    this test suite); a product process gets DEVIS_MSDA_ERR_UNSUPPORTED and keeps the built-in kernel selection"""
+    import subprocess
+    import sys
+    code = ("import sys\nsys.path.insert(0, %r)\nfrom devis_b200 import _lib\n"
+            "print('RC', _lib.load().devis_msda_set_tuning(0, 128))\n" % ROOT)
+    env = {k: v for k, v in os.environ.items() if k != "DEVIS_MSDA_TUNING"}
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300).stdout
+    assert "RC -8" in out, out
+    out = subprocess.run([sys.executable, "-c", code], env=dict(env, DEVIS_MSDA_TUNING="1"), capture_output=True,
+                         text=True, timeout=300).stdout
+    assert "RC 0" in out, out
 
 
 def test_product_package_never_imports_the_oracle():

@@ -59,25 +59,26 @@ def test_c_oracle_handles_empty_query_set():
 
 
 def _sd(g):
-    return {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    # the d32p4 fixtures store their (bfloat16-representable) parameters and inputs as float32
+    return {k[3:]: torch.from_numpy(v).double() for k, v in g.items() if k.startswith("sd.")}
 
 
-@pytest.mark.parametrize("tag", ["all", "window"])
+@pytest.mark.parametrize("tag", ["all", "window", "d32p4_all", "d32p4_window"])
 def test_temporal_encoder_port_matches_reference_module(tag):
     g = load_golden(f"mod_tenc_{tag}")
     t_frames, c, nl, t_window, heads, pc, pt = [int(x) for x in g["cfg"]]
-    t = lambda k: torch.from_numpy(g[k])
+    t = lambda k: torch.from_numpy(g[k]).double() if g[k].dtype.kind == "f" else torch.from_numpy(g[k])
     offs = [row for row in t("temporal_offsets")]
     out = temporal_torch.temporal_encoder_forward(_sd(g), t("query"), t("ref"), t("inp"), t("shapes"), offs,
                                                   heads, nl, t_window, pc, pt)
     assert nmax(out.numpy(), g["out"]) < 1e-12
 
 
-@pytest.mark.parametrize("tag", ["2d_ia", "2d_noia", "4d_ia", "4d_noia"])
+@pytest.mark.parametrize("tag", ["2d_ia", "2d_noia", "4d_ia", "4d_noia", "d32p4_2d", "d32p4_4d"])
 def test_temporal_decoder_port_matches_reference_module(tag):
     g = load_golden(f"mod_tdec_{tag}")
     t_frames, c, nl, t_window, heads, pc, pt, ia = [int(x) for x in g["cfg"]]
-    t = lambda k: torch.from_numpy(g[k])
+    t = lambda k: torch.from_numpy(g[k]).double() if g[k].dtype.kind == "f" else torch.from_numpy(g[k])
     offs = [row for row in t("temporal_offsets")]
     out, lc, lt, awc, awt = temporal_torch.temporal_decoder_forward(
         _sd(g), t("query"), t("ref"), t("inp"), t("shapes"), offs, heads, nl, t_window, pc, pt, bool(ia))

@@ -466,87 +466,6 @@ def test_bf16_grad_value_accumulation_fused_encoder_module():
     assert nmax(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) < 5e-2
 
 
-def test_experimental_windowed_backward_matches_direct_scatter():
-    """msda_bwd_win.cuh (tuning key 6 = 2, off by default): grad_value pre-aggregated per block in 32-bit fixed point.
-    Against the direct-scatter kernel at the full DeVIS shape: grad_value within the north-star 1e-4 (measured 2.3e-5,
-    rms 1e-6), every other gradient bit-identical; and against the fp64 oracle on a small clip."""
-    from devis_b200 import _lib, synthetic
-    from oracle import temporal_torch
-    clip = synthetic.make_clip(dist="local", seed=5, device="cuda")
-    geom_order = None
-    try:
-        from devis_b200 import clip_geometry
-        geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
-        geom_order = geom.tile_order("cuda")
-        _, direct, _ = _clip_fn(clip, order=geom_order)
-        _lib.set_tuning(6, 2)
-        _, windowed, _ = _clip_fn(clip, order=geom_order)
-        assert nmax(windowed[0].cpu().numpy(), direct[0].cpu().numpy()) < 1e-4
-        for a, b in zip(windowed[1:], direct[1:]):
-            assert torch.equal(a, b)
-        # uniform taps (windows rarely hit), ragged small pyramid, and the oracle
-        shapes = ((18, 30), (9, 15), (5, 8))
-        small = synthetic.make_clip(n_frames=4, shapes=shapes, queries=None, dist="local", seed=3, device="cuda")
-        g2 = clip_geometry.ClipGeometry(shapes, 4, small["frame_table"])
-        _, grads, _ = _clip_fn(small, order=g2.tile_order("cuda"))
-    finally:
-        _lib.set_tuning(6, 0)
-    cpu = {k: (v.detach().double().cpu() if isinstance(v, torch.Tensor) else v) for k, v in small.items()}
-    leaves = [cpu[k].clone().requires_grad_(True) for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
-    offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(small["frame_table"])]
-    ref = temporal_torch.temporal_core_per_frame(*leaves, torch.tensor(shapes), offs)
-    ref.backward(cpu["grad_out"])
-    for got, leaf in zip(grads, leaves):
-        assert nmax(got.cpu().numpy(), leaf.grad.numpy()) < 1e-4
-
-
-def test_sorted_backward_matches_direct_scatter():
-    """msda_bwd_sort.cuh (tuning key 6 = 3): grad_value contributions of an 8 x 8 query tile counting-sorted by target
-    row in shared memory and reduced run by run.  Against the direct-scatter kernel at the full DeVIS shape: grad_value
-    within the north-star 1e-4 (only the order of the float sums differs), every other gradient bit-identical; then
-    uniform taps (most taps miss their window), narrow margins, windows on the coarse levels only, a ragged small
-    pyramid against the fp64 oracle, and bf16 value."""
-    from devis_b200 import _lib, clip_geometry, synthetic
-    from oracle import temporal_torch
-    try:
-        for dist, margin, min_level in (("local", 0, 0), ("local", 1, 0), ("local", 12, 0), ("local", 0, 3), ("uniform", 0, 0)):
-            clip = synthetic.make_clip(dist=dist, seed=5, device="cuda")
-            geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
-            order = geom.tile_order("cuda")
-            _lib.set_tuning(6, 1)
-            _, direct, _ = _clip_fn(clip, order=order)
-            _lib.set_tuning(6, 3); _lib.set_tuning(7, margin); _lib.set_tuning(9, min_level)
-            _, srt, _ = _clip_fn(clip, order=order)
-            assert nmax(srt[0].cpu().numpy(), direct[0].cpu().numpy()) < 1e-5, (dist, margin, min_level)
-            for a, b in zip(srt[1:], direct[1:]):
-                assert torch.equal(a, b)
-        _lib.set_tuning(7, 0); _lib.set_tuning(9, 0)
-        # bf16 value (float grad_value)
-        clip = synthetic.make_clip(dist="local", seed=6, device="cuda", dtype=torch.bfloat16)
-        geom = clip_geometry.ClipGeometry(clip["shapes"], 6, clip["frame_table"])
-        _lib.set_tuning(6, 1)
-        _, direct, _ = _clip_fn(clip, order=geom.tile_order("cuda"))
-        _lib.set_tuning(6, 3)
-        _, srt, _ = _clip_fn(clip, order=geom.tile_order("cuda"))
-        assert nmax(srt[0].float().cpu().numpy(), direct[0].float().cpu().numpy()) < 1e-2
-        for a, b in zip(srt[1:], direct[1:]):
-            assert torch.equal(a, b)
-        # ragged small pyramid (partial tiles, 4 levels) against the fp64 oracle
-        shapes = ((18, 30), (9, 15), (5, 8), (3, 4))
-        small = synthetic.make_clip(n_frames=4, shapes=shapes, queries=None, dist="local", seed=3, device="cuda")
-        g2 = clip_geometry.ClipGeometry(shapes, 4, small["frame_table"])
-        _, grads, _ = _clip_fn(small, order=g2.tile_order("cuda"))
-    finally:
-        _lib.set_tuning(6, 0); _lib.set_tuning(7, 0); _lib.set_tuning(9, 0)
-    cpu = {k: (v.detach().double().cpu() if isinstance(v, torch.Tensor) else v) for k, v in small.items()}
-    leaves = [cpu[k].clone().requires_grad_(True) for k in ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")]
-    offs = [torch.tensor([f - t for f in row]) for t, row in enumerate(small["frame_table"])]
-    ref = temporal_torch.temporal_core_per_frame(*leaves, torch.tensor(shapes), offs)
-    ref.backward(cpu["grad_out"])
-    for got, leaf in zip(grads, leaves):
-        assert nmax(got.cpu().numpy(), leaf.grad.numpy()) < 1e-4
-
-
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_deterministic_sorted_backward_is_bit_identical_to_direct_deterministic_scatter(dtype):
     """Deterministic mode in the encoder form (query order given) runs msda_bwds_kernel<DET>: the same 64-bit fixed-point
