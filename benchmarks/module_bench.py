@@ -187,8 +187,25 @@ def main():
                 return run
 
             key = f"decoder_layer_attention_T6_q{q}_ref{ref_dim}d"
-            row = {"ours_fwd_bwd_ms": med_ms(d_ours), "ours_fwd_ms": med_ms(d_ours_fwd),
-                   "per_frame_loop_with_our_dropin_op_fwd_bwd_ms": med_ms(d_ref(MSDeformAttnFunction.apply))}
+            row = {"ours_fwd_bwd_ms": med_ms(d_ours), "ours_fwd_ms": med_ms(d_ours_fwd)}
+            dec.fuse_prologue = False
+            row["ours_unfused_prologue_fwd_bwd_ms"] = med_ms(d_ours)
+            dec.fuse_prologue = True
+            row["per_frame_loop_with_our_dropin_op_fwd_bwd_ms"] = med_ms(d_ref(MSDeformAttnFunction.apply))
+            # product path for fixed shapes: devis_b200.GraphedLayer (forward and backward graphs, autograd-integrated)
+            try:
+                from devis_b200 import GraphedLayer
+                import copy
+                gl = GraphedLayer(copy.deepcopy(dec), *args)
+                g_q = dq.detach().clone().requires_grad_(True)
+
+                def d_graphed():
+                    gl(g_q, dref, inp, (shapes, tshapes), (lsi, tlsi), offsets)[0].backward(dgout)
+
+                row["ours_graphed_layer_fwd_bwd_ms"] = med_ms(d_graphed)
+                del gl
+            except Exception as exc:   # noqa: BLE001
+                row["ours_graphed_layer_fwd_bwd_ms"] = f"failed: {str(exc)[:160]}"
             if RefFunction.mod is not None:
                 row["reference_loop_with_reference_cuda_op_fwd_bwd_ms"] = med_ms(d_ref(RefFunction.apply))
                 row["reference_loop_with_reference_cuda_op_fwd_ms"] = med_ms(d_ref(RefFunction.apply, False))

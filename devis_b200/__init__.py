@@ -7,6 +7,7 @@ acaelles97/DeVIS (src/models/ops), behind the reference's own Python API.
   devis_b200.modules.*                       MSDeformAttn, TemporalMSDeformAttn{Encoder,Decoder}
   devis_b200.devis_transformer               DeVISTransformer and its encoder / decoder (layers): the direct callers
   devis_b200.clip_geometry                   host-side level / frame tables for the whole-clip op
+  devis_b200.GraphedLayer                    CUDA-graph replay (forward + backward) of a layer for fixed shapes
   devis_b200.build                           nvcc recipe for libdevis_msda.so (include/devis_msda.h)
 
 There is no CPU or PyTorch fallback: the ops raise if libdevis_msda.so is absent.
@@ -17,10 +18,11 @@ from .functions import (MSDeformAttnFunction, TemporalMSDeformAttnFunction,  # n
                         TemporalMSDeformAttnFusedFunction, temporal_ms_deform_attn)
 from .modules import (MSDeformAttn, TemporalMSDeformAttnBase, TemporalMSDeformAttnDecoder,  # noqa: F401
                       TemporalMSDeformAttnEncoder)
+from .graphed import GraphedLayer  # noqa: F401
 from .devis_transformer import (DeVISTransformer, DeVISTransformerDecoder, DeVISTransformerDecoderLayer,  # noqa: F401
                                 DeVISTransformerEncoder, DeVISTransformerEncoderLayer)
 
 __all__ = ["MSDeformAttnFunction", "TemporalMSDeformAttnFunction", "TemporalMSDeformAttnFusedFunction", "temporal_ms_deform_attn", "MSDeformAttn",
            "TemporalMSDeformAttnBase", "TemporalMSDeformAttnEncoder", "TemporalMSDeformAttnDecoder",
            "MultiScaleDeformableAttention", "clip_geometry", "DeVISTransformer", "DeVISTransformerEncoder",
-           "DeVISTransformerEncoderLayer", "DeVISTransformerDecoder", "DeVISTransformerDecoderLayer"]
+           "DeVISTransformerEncoderLayer", "DeVISTransformerDecoder", "DeVISTransformerDecoderLayer", "GraphedLayer"]

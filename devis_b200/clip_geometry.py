@@ -66,9 +66,15 @@ class ClipGeometry:
     def tile_order(self, device, tile_h=8, tile_w=8):
         """Permutation of the S pixel-queries of one frame (encoder self-attention: query i is pixel i,
         deformable_transformer.py:184-198) that walks every level in tile_h x tile_w tiles.  Only
-        meaningful when num_query == spatial_size and levels are stored back to back."""
+        meaningful when num_query == spatial_size and levels are stored back to back: returns None otherwise (the
+        caller then visits the queries in index order -- the order only affects cache locality)."""
         key = (str(device), tile_h, tile_w)
         if key not in self._orders:
+            areas = [h * w for h, w in self.shapes]
+            packed = all(st == sum(areas[:i]) for i, st in enumerate(self.level_start_index))
+            if not packed or sum(areas) != self.spatial_size:
+                self._orders[key] = None
+                return None
             order = []
             for (h, w), start in zip(self.shapes, self.level_start_index):
                 idx = np.arange(h * w, dtype=np.int64).reshape(h, w) + start
@@ -76,8 +82,6 @@ class ClipGeometry:
                     for x0 in range(0, w, tile_w):
                         order.append(idx[y0:y0 + tile_h, x0:x0 + tile_w].reshape(-1))
             perm = np.concatenate(order).astype(np.int32)
-            assert np.array_equal(np.sort(perm), np.arange(self.spatial_size, dtype=np.int32)), \
-                "tile order needs back-to-back levels"
             self._orders[key] = torch.from_numpy(perm).to(device)
         return self._orders[key]
 
@@ -176,6 +180,23 @@ def from_reference_args(n_frames, input_spatial_shapes, input_level_start_index,
     lsi = tuple(_host_list(cur_lsi))
     offs = _offsets_table(temporal_offsets)
     table = tuple(tuple(int(o) + t for o in row) for t, row in enumerate(offs))
+    # The whole-clip op derives the temporal halves of the pairs itself (every sampled frame has the query frame's
+    # pyramid, laid out like it: what devis_transformer.py:97,118,153-154 builds).  The reference honours whatever it is
+    # handed, so anything else must be refused, not silently mis-evaluated.  Read once per tensor object (memoised).
+    wt = len(table[0]) if table else 0
+    if isinstance(input_spatial_shapes, (tuple, list)) and len(input_spatial_shapes) > 1 and wt \
+            and input_spatial_shapes[1] is not None:
+        tshapes = tuple(tuple(r) for r in _host_list(input_spatial_shapes[1]))
+        if tshapes != shapes * wt:
+            raise RuntimeError("temporal spatial shapes must be the current shapes repeated t_window times "
+                               f"(got {tshapes}, current {shapes}, t_window {wt})")
+    if isinstance(input_level_start_index, (tuple, list)) and len(input_level_start_index) > 1 and wt \
+            and input_level_start_index[1] is not None:
+        tlsi = tuple(_host_list(input_level_start_index[1]))
+        frame_rows = max(st + h * w for st, (h, w) in zip(lsi, shapes))
+        if tlsi != tuple(j * frame_rows + st for j in range(wt) for st in lsi):
+            raise RuntimeError("temporal level_start_index must be the per-frame start indices offset by one frame's rows "
+                               "per temporal slot")
     key = (n_frames, shapes, lsi, table)
     geom = _geom_cache.get(key)
     if geom is None:

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
     const int grp = threadIdx.x / LPG;
     const int QC = blockDim.x / LPG;
     const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+    const L2Policy pol = make_l2_policy();
 
     int q[QPG];
     bool qlive[QPG];
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
         if (qlive[i]) {
             const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
             go[i] = BF16 ? ldg_bf16x4(reinterpret_cast<const uint2 *>(a.grad_out) + row * LPG + j)
-                         : ldg_f4(reinterpret_cast<const float4 *>(a.grad_out) + row * LPG + j);
+                         : ld_stream_f4(reinterpret_cast<const float4 *>(a.grad_out) + row * LPG + j, pol);
         }
     }
 
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                 float2 xy = make_float2(0.f, 0.f);
                 float w = 0.f;
                 if (live) {
-                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                    w = ld_stream_f(aw + row * K + k);
+                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k, pol);
+                    w = ld_stream_f(aw + row * K + k, pol);
                 }
                 const TapGeom t = tap_geometry(xy.x, xy.y, sl, live);
                 float *buf = xbuf + parity * X::kWordsPerWarpBuf;
@@ -164,10 +165,10 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                         v10 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.z));
                         v11 = ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + off.w));
                     } else {
-                        v00 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.x));
-                        v01 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.y));
-                        v10 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.z));
-                        v11 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.w));
+                        v00 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.x), pol);
+                        v01 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.y), pol);
+                        v10 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.z), pol);
+                        v11 = ldg_f4(reinterpret_cast<const float4 *>(vbase + off.w), pol);
                     }
                     dsum[jj][0] = fmaf(v00.w, gg.w, fmaf(v00.z, gg.z, fmaf(v00.y, gg.y, v00.x * gg.x)));
                     dsum[jj][1] = fmaf(v01.w, gg.w, fmaf(v01.z, gg.z, fmaf(v01.y, gg.y, v01.x * gg.x)));
@@ -179,10 +180,10 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                         if (c.z != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.z << (kGvShift + 1))), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
                         if (c.w != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.w << (kGvShift + 1))), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
                     } else if (gvb) {
-                        if (c.x != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.x << kGvShift), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
-                        if (c.y != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.y << kGvShift), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
-                        if (c.z != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.z << kGvShift), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
-                        if (c.w != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.w << kGvShift), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                        if (c.x != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.x << kGvShift), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w, pol);
+                        if (c.y != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.y << kGvShift), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w, pol);
+                        if (c.z != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.z << kGvShift), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w, pol);
+                        if (c.w != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.w << kGvShift), c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w, pol);
                     }
                 }
 
@@ -199,9 +200,9 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) msda_bwd_kernel(con
                     const float val = hh * (hw * A[0] + lw * A[1]) + lh * (hw * A[2] + lw * A[3]);
                     const float gx = hh * (r_in * A[1] - l_in * A[0]) + lh * (r_in * A[3] - l_in * A[2]);
                     const float gy = hw * (b_in * A[2] - t_in * A[0]) + lw * (b_in * A[3] - t_in * A[1]);
-                    st_stream_f(gaw + row * K + k, hit ? val : 0.f);
+                    st_stream_f(gaw + row * K + k, hit ? val : 0.f, pol);
                     st_stream_f2(reinterpret_cast<float2 *>(gloc + row * K * 2) + k,
-                                 hit ? make_float2((float)sl.y * gx * w, (float)sl.x * gy * w) : make_float2(0.f, 0.f));
+                                 hit ? make_float2((float)sl.y * gx * w, (float)sl.x * gy * w) : make_float2(0.f, 0.f), pol);
                 }
             }
         }

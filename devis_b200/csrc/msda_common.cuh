@@ -253,6 +253,103 @@ __device__ __forceinline__ void st_stream_f(float *p, float v)
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// L2 residency hints (the backward moved 1025 MB through DRAM against 622 MB of
+// algorithmic bytes because 592 MB of single-use streams pushed value / grad_value, 59 MB together, out of the 126 MB
+// L2 and the reduction's read-modify-write lines were fetched again).  createpolicy descriptors, sm_80+:
+//   DEVIS_L2_HINTS bit 0: single-use streams (locations, weights, grad_out; outputs, grad_loc, grad_aw) -> L2::evict_first
+//   bit 1: value gathers -> L2::evict_last        bit 2: grad_value reductions -> L2::evict_last
+// Compile-time A/B like DEVIS_HINTS (benchmarks/build_variants.py).  MEASURED (round 2, profiles/r2a_l2_hints.json): no
+// effect -- backward 1429-1430 us and 994-1013 MB of DRAM traffic for every combination (0, 1, 4, 6, 7), forward 516 us
+// and 318-325 MB: the descriptors do not keep the reduction targets resident, and DRAM (9 % busy) is not what the kernel
+// waits for anyway.  Default 0 (the policies would cost the 80-register backward an 8-byte spill for nothing).
+// ---------------------------------------------------------------------------------------------
+#ifndef DEVIS_L2_HINTS
+#define DEVIS_L2_HINTS 0
+#endif
+
+struct L2Policy {
+    unsigned long long stream;   // evict_first
+    unsigned long long keep;     // evict_last
+};
+
+__device__ __forceinline__ L2Policy make_l2_policy()
+{
+    L2Policy p;
+    p.stream = 0ull;
+    p.keep = 0ull;
+#if DEVIS_L2_HINTS & 1
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+#endif
+#if DEVIS_L2_HINTS & 6
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+#endif
+    return p;
+}
+
+__device__ __forceinline__ float2 ld_stream_f2(const float2 *p, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 1
+    float2 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol.stream));
+    return v;
+#else
+    return ld_stream_f2(p);
+#endif
+}
+
+__device__ __forceinline__ float ld_stream_f(const float *p, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 1
+    float v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol.stream));
+    return v;
+#else
+    return ld_stream_f(p);
+#endif
+}
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 1
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol.stream));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
+__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 1
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w), "l"(pol.stream) : "memory");
+#else
+    st_stream_f4(p, v);
+#endif
+}
+
+__device__ __forceinline__ void st_stream_f2(float2 *p, float2 v, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 1
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "l"(pol.stream) : "memory");
+#else
+    st_stream_f2(p, v);
+#endif
+}
+
+__device__ __forceinline__ void st_stream_f(float *p, float v, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 1
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol.stream) : "memory");
+#else
+    st_stream_f(p, v);
+#endif
+}
+
 // 16-byte read-only loads / vector reductions --------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float4 *p)
 {
@@ -262,6 +359,18 @@ __device__ __forceinline__ float4 ldg_f4(const float4 *p)
     return v;
 #else
     return __ldg(p);
+#endif
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float4 *p, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 2
+    float4 v;
+    asm("ld.global.nc.L1::evict_last.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol.keep));
+    return v;
+#else
+    return ldg_f4(p);
 #endif
 }
 
@@ -291,11 +400,28 @@ __device__ __forceinline__ void red_add_bf16x4(void *p, float a, float b, float 
                  : "memory");
 }
 
+__device__ __forceinline__ void red_add_f4(float *p, float a, float b, float c, float d, const L2Policy &pol)
+{
+#if DEVIS_L2_HINTS & 4
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d),
+                 "l"(pol.keep) : "memory");
+#else
+    red_add_f4(p, a, b, c, d);
+#endif
+}
+
 template <bool HALF>
 __device__ __forceinline__ void red_add_quad(char *p, float a, float b, float c, float d)
 {
     if (HALF) red_add_bf16x4(p, a, b, c, d);
     else red_add_f4(reinterpret_cast<float *>(p), a, b, c, d);
+}
+
+template <bool HALF>
+__device__ __forceinline__ void red_add_quad(char *p, float a, float b, float c, float d, const L2Policy &pol)
+{
+    if (HALF) red_add_bf16x4(p, a, b, c, d);
+    else red_add_f4(reinterpret_cast<float *>(p), a, b, c, d, pol);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -197,7 +197,7 @@ __device__ __forceinline__ void decode_tap16(const uint4 r, unsigned rowbytes, u
 // one exchange of 8 published records -> 32 corner gathers and 128 FFMA per lane (8 lanes x 4 channels per row)
 template <bool BF16>
 __device__ __forceinline__ void consume_tap16x8(const float *buf, int g, unsigned rowbytes, unsigned pitch_lo,
-                                                unsigned pitch_hi, const char *vbase, float4 &acc)
+                                                unsigned pitch_hi, const char *vbase, float4 &acc, const L2Policy &pol)
 {
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += 2) {
@@ -213,7 +213,7 @@ __device__ __forceinline__ void consume_tap16x8(const float *buf, int g, unsigne
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 v[u][e] = BF16 ? ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + o[u][e]))
-                               : ldg_f4(reinterpret_cast<const float4 *>(vbase + o[u][e]));
+                               : ldg_f4(reinterpret_cast<const float4 *>(vbase + o[u][e]), pol);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             acc.x = fmaf(c[u][3], v[u][3].x, fmaf(c[u][2], v[u][2].x, fmaf(c[u][1], v[u][1].x, fmaf(c[u][0], v[u][0].x, acc.x))));
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
     const int M = a.d.M, Lq = a.d.Lq;
     const int j = threadIdx.x & 7, g = (threadIdx.x & 31) >> 3, grp = threadIdx.x >> 3, QC = blockDim.x >> 3;
     const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+    const L2Policy pol = make_l2_policy();
 
     int q[QPG];
     bool qlive[QPG];
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
             in[i].xy = make_float2(0.f, 0.f);
             in[i].w = 0.f;
             if (k < K && qlive[i]) {
-                in[i].xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                in[i].w = ld_stream_f(aw + row * K + k);
+                in[i].xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k, pol);
+                in[i].w = ld_stream_f(aw + row * K + k, pol);
             }
         }
     };
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
                 parity ^= 1;
                 *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, cur[i].w, rowbytes);
                 __syncwarp();
-                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i]);
+                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], pol);
             }
         }
         slot_base += a.seg[sg].n_slots;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
         if (BF16)
             reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc[i]);
         else
-            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row * LPG + j, acc[i]);
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row * LPG + j, acc[i], pol);
     }
 }
 

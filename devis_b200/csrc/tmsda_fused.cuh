@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
     const int M = a.d.M, Lq = a.d.Lq;
     const int j = threadIdx.x % LPG, g = (threadIdx.x & 31) / LPG, grp = threadIdx.x / LPG, QC = blockDim.x / LPG;
     const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+    const L2Policy pol = make_l2_policy();
     bool qlive[QPG];
     size_t qrow[QPG], row[QPG];
 #pragma unroll
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
                 parity ^= 1;
                 *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
                 __syncwarp();
-                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i]);
+                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], pol);
             }
         }
         slot_base += a.n_slots[sg];

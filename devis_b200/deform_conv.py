@@ -26,7 +26,8 @@ Two forms (both hand-written kernels of this library, chosen per layer by ``devi
 Supported: groups == 1 and offset_groups == 1 (everything DeVIS uses), float32 / float64 (half and bfloat16 are
 computed in float32 like torchvision's autocast wrapper does), CUDA only -- there is no CPU fallback.
 """
-import weakref
+
+import warnings
 
 import torch
 from torch.autograd import Function
@@ -47,8 +48,26 @@ def _out_size(size, k, stride, pad, dil):
 
 
 _FUSED = True
+_warned_nondeterministic = False
+
+
+def _alert_not_deterministic():
+    """grad_input is scattered with float ``red.global.add`` (fused backward and devis_dcn_col2im alike): the sum order,
+    hence the last bits, change from run to run -- unlike the attention op, the deformable convolution has no
+    fixed-point mode.  Under ``torch.use_deterministic_algorithms(True)`` say so, the way ATen's non-deterministic
+    kernels do (error, or a warning in warn_only mode); only the WEIGHT gradient is rerouted to a deterministic GEMM."""
+    global _warned_nondeterministic
+    if not torch.are_deterministic_algorithms_enabled():
+        return
+    msg = ("devis_b200.deform_conv2d backward does not have a deterministic implementation for grad_input (float atomic "
+           "scatter), but you set 'torch.use_deterministic_algorithms(True)'")
+    if torch.is_deterministic_algorithms_warn_only_enabled():
+        if not _warned_nondeterministic:
+            warnings.warn(msg, stacklevel=3)
+            _warned_nondeterministic = True
+        return
+    raise RuntimeError(msg + ". You can turn off determinism just for this operation, or use warn_only=True.")
 _COLS_CHUNK_BYTES = 256 << 20          # recomputed columns per weight-gradient chunk
-_packed_cache = {}
 
 
 def _wgrad(g2, cols):
@@ -84,10 +103,10 @@ def _fused_form(c, cout, kh, kw, dtype):
 
 
 def _packed_weight(weight):
-    """weight (Cout, Cin, kh, kw) in the layout the fused kernels read; cached per tensor object and version"""
-    hit = _packed_cache.get(id(weight))
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
-        return hit[2]
+    """weight (Cout, Cin, kh, kw) in the layout the fused kernels read.  Repacked on EVERY call: one small kernel over
+    <= 100 KB for the layers the fused form serves.  (Round 1 cached the packed copy per tensor object and ``_version``;
+    writes through ``Parameter.data`` -- ``nn.Module.to()``, EMA / weight-swap code -- do not bump ``_version``, so the
+    fused path could run with stale weights, or with a pointer on the wrong device after ``model.to('cuda:1')``.)"""
     cout, c, kh, kw = weight.shape
     lib = _lib.load()
     w = weight.detach()
@@ -95,9 +114,6 @@ def _packed_weight(weight):
     packed = torch.empty(int(lib.devis_dcn_packed_weight_elems(c, cout, kh, kw)), dtype=torch.float32, device=weight.device)
     with torch.cuda.device(weight.device):
         _lib.check(lib.devis_dcn_pack_weight(_ptr(w), _ptr(packed), c, cout, kh, kw, torch.cuda.current_stream().cuda_stream))
-    if len(_packed_cache) >= 64:
-        _packed_cache.clear()
-    _packed_cache[id(weight)] = (weakref.ref(weight), weight._version, packed)
     return packed
 
 
@@ -144,6 +160,8 @@ class FusedDeformConv2dFunction(Function):
         stream = torch.cuda.current_stream().cuda_stream
         with torch.cuda.device(x.device):
             if need_in or need_off or (need_m and mask is not None):
+                if need_in:
+                    _alert_not_deterministic()
                 gx = torch.empty_like(x) if need_in else None
                 grad_off = torch.empty_like(offset)
                 grad_m = torch.empty_like(mask) if mask is not None else None
@@ -234,6 +252,8 @@ class DeformConv2dFunction(Function):
             grad_b = g2.sum(0)
         if need_in or need_off or (need_m and mask is not None):
             grad_cols = g2 @ w2
+            if need_in:
+                _alert_not_deterministic()
             gx = torch.empty_like(x) if need_in else None
             grad_off = torch.empty_like(offset)
             grad_m = torch.empty_like(mask) if mask is not None else None

@@ -280,4 +280,7 @@ class DeVISTransformer(nn.Module):
             h, w = lvl_src.shape[-2:]
             memories.append(memory[:, start:start + h * w].permute(2, 0, 1).view(1, channels, n_frames, h, w))
             start += h * w
-        return hs, query_embed, memories, reference_points, inter_references, level_start_index, valid_ratios, spatial_shapes
+        # the pyramid tensors are process-cached (clip_geometry.pyramid_tensors): hand the caller its own copies, so an
+        # in-place edit there cannot corrupt later forwards with the same image size
+        return (hs, query_embed, memories, reference_points, inter_references, level_start_index.clone(), valid_ratios,
+                spatial_shapes.clone())

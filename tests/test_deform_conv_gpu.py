@@ -132,6 +132,27 @@ def test_fused_forward_without_grad_and_partial_grads():
     assert nmax(off.grad.cpu().numpy(), g["goffset"]) < 1e-4
 
 
+def test_fused_path_sees_weight_changes_made_through_parameter_data():
+    """writes through ``Parameter.data`` (nn.Module.to, EMA / weight-swap code) do not bump
+    ``_version``; the fused path must still read the CURRENT weight -- it repacks on every call"""
+    from devis_b200.deform_conv import deform_conv2d
+    g = load_golden("dcn_fused_c32_o16")
+    t = lambda k: torch.from_numpy(g[k]).to("cuda", torch.float32)
+    w = torch.nn.Parameter(t("weight"))
+    args = (t("x"), t("offset"))
+    with torch.no_grad():
+        first = deform_conv2d(*args, w, t("bias"), padding=1, mask=t("mask"))
+        version = w._version
+        w.data.mul_(2.0)                                   # in place through .data: _version unchanged
+        assert w._version == version
+        second = deform_conv2d(*args, w, None, padding=1, mask=t("mask"))
+        w.data = t("weight") * 3.0                         # set_data: what Module.to() / .cuda() do
+        third = deform_conv2d(*args, w, None, padding=1, mask=t("mask"))
+    base = first - t("bias").view(1, -1, 1, 1)
+    assert nmax(second.cpu().numpy(), (2.0 * base).cpu().numpy()) < 1e-6
+    assert nmax(third.cpu().numpy(), (3.0 * base).cpu().numpy()) < 1e-6
+
+
 def test_half_inputs_are_computed_in_float32_and_cast_back():
     g = load_golden("dcn_k3_c24")
     from devis_b200.deform_conv import deform_conv2d
