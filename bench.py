@@ -483,8 +483,8 @@ def train_trunk_leg(torch, dist_mod, dev, rank, world, local_rank, steps=8, warm
             super().__init__()
             self.m = model
 
-        def forward(self):
-            hs, _, memories, *_ = self.m["trunk"](srcs, masks, pos, self.m["query_embed"].weight)
+        def forward(self, level0):                    # DDP wants at least one tensor argument
+            hs, _, memories, *_ = self.m["trunk"]([level0] + srcs[1:], masks, pos, self.m["query_embed"].weight)
             return hs, memories
 
     net = Step()
@@ -498,11 +498,11 @@ def train_trunk_leg(torch, dist_mod, dev, rank, world, local_rank, steps=8, warm
         runner = ddp if ddp is not None else net
         if ddp is not None and not sync:
             with ddp.no_sync():
-                hs, memories = runner()
+                hs, memories = runner(srcs[0])
                 loss = hs[-1].float().square().mean() + 1e-3 * sum(m.float().square().mean() for m in memories)
                 loss.backward()
         else:
-            hs, memories = runner()
+            hs, memories = runner(srcs[0])
             loss = hs[-1].float().square().mean() + 1e-3 * sum(m.float().square().mean() for m in memories)
             loss.backward()
         torch.nn.utils.clip_grad_norm_(net.parameters(), 0.1)
@@ -800,7 +800,8 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.empty_cache()
             extra["train_trunk"] = train_trunk_leg(torch, dist_mod, dev, rank, world, local_rank)
         except Exception as exc:   # noqa: BLE001
-            extra["train_trunk"] = {"error": str(exc)[:300]}
+            import traceback
+            extra["train_trunk"] = {"error": str(exc)[:300], "where": traceback.format_exc()[-700:]}
 
     if rank == 0:
         bwd_kernel = "msda_bwd_kernel"

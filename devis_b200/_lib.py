@@ -19,7 +19,8 @@ FLAG_DETERMINISTIC, FLAG_NO_GRAD_VALUE, FLAG_BF16_GRAD_VALUE = 1, 2, 4
 TREF_LEVEL0, TREF_OWN, TREF_SAMPLED = 0, 1, 2
 # kernel families of devis_msda_kernel_launches (DEVIS_MSDA_KERNEL_*)
 KERNEL_FWD_GROUPED, KERNEL_FWD_GENERIC, KERNEL_BWD_GROUPED, KERNEL_BWD_GENERIC = 0, 1, 2, 3
-KERNEL_FUSED_FWD, KERNEL_FUSED_BWD, KERNEL_BWD_SORTED, KERNEL_AUX, KERNEL_DCN = 4, 5, 6, 7, 8
+KERNEL_FUSED_FWD, KERNEL_FUSED_BWD, KERNEL_BWD_SORTED, KERNEL_AUX, KERNEL_DCN, KERNEL_DCN_IGEMM = 4, 5, 6, 7, 8, 9
+DCN_PRECISION_3XTF32, DCN_PRECISION_TF32 = 0, 1
 
 _vp, _i, _u, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
 
@@ -49,6 +50,10 @@ SIGNATURES = {
     "devis_dcn_fused_backward": (_i, [_vp] * 8 + [_i] * 15 + [_vp]),
     "devis_dcn_wgrad_supported": (_i, [_i] * 5),
     "devis_dcn_weight_grad": (_i, [_vp] * 5 + [_i] * 15 + [_vp]),
+    "devis_dcn_igemm_supported": (_i, [_i] * 5),
+    "devis_dcn_igemm_packed_weight_elems": (_sz, [_i] * 4),
+    "devis_dcn_igemm_pack_weight": (_i, [_vp] * 2 + [_i] * 4 + [_vp]),
+    "devis_dcn_igemm_forward": (_i, [_vp] * 6 + [_i] * 16 + [_vp]),
 }
 
 _lib = None

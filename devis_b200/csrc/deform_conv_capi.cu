@@ -2,6 +2,7 @@
 #include "../../include/devis_deform_conv.h"
 #include "capi_common.h"
 #include "deform_conv.cuh"
+#include "dcn_igemm.cuh"
 
 #include <mutex>
 
@@ -414,6 +415,118 @@ int devis_dcn_weight_grad(const void *input, const void *offset, const void *mas
         if (rc2) return rc2;
     }
     return DEVIS_MSDA_OK;
+}
+
+
+// ---- tensor-core implicit GEMM forward (dcn_igemm.cuh) -----------------------------------------------------------------
+namespace {
+
+struct IgPlan {
+    bool ok = false;
+    int Npad = 0, nchunks = 0, n0 = 0, n1 = 0, tmem_cols = 0;
+    int stages(int split) const
+    {
+        const int stage = (split ? 2 : 1) * (devis::kIgATile + Npad * 128);
+        int s = (227 * 1024 - devis::kIgGeomBytes - 256 - 1024) / stage;
+        return s > devis::kIgMaxStages ? devis::kIgMaxStages : s;
+    }
+    size_t smem(int split) const
+    {
+        return (size_t)stages(split) * (split ? 2 : 1) * (devis::kIgATile + Npad * 128) + devis::kIgGeomBytes + 256 + 1024;
+    }
+};
+
+IgPlan igemm_plan(int channels, int out_channels, int kernel_h, int kernel_w, int dtype)
+{
+    IgPlan p;
+    if (dtype != DEVIS_MSDA_F32 || channels <= 0 || out_channels <= 0 || kernel_h <= 0 || kernel_w <= 0) return p;
+    if (channels % 8 != 0 || out_channels % 4 != 0) return p;
+    p.Npad = (out_channels + 15) / 16 * 16;
+    if (p.Npad > 512) return p;
+    p.nchunks = (channels + devis::kIgBK - 1) / devis::kIgBK;
+    if (p.Npad <= 256) {
+        p.n0 = p.Npad;
+    } else {                                  // two MMAs along N, both multiples of 16 and <= 256
+        p.n0 = (p.Npad / 2 + 15) / 16 * 16;
+        p.n1 = p.Npad - p.n0;
+    }
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.Npad) p.tmem_cols *= 2;
+    p.ok = p.stages(1) >= 2;
+    return p;
+}
+
+}  // namespace
+
+int devis_dcn_igemm_supported(int channels, int out_channels, int kernel_h, int kernel_w, int dtype)
+{
+    return igemm_plan(channels, out_channels, kernel_h, kernel_w, dtype).ok ? 1 : 0;
+}
+
+size_t devis_dcn_igemm_packed_weight_elems(int channels, int out_channels, int kernel_h, int kernel_w)
+{
+    const IgPlan p = igemm_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    return p.ok ? (size_t)kernel_h * kernel_w * p.nchunks * 2 * p.Npad * devis::kIgBK : 0;
+}
+
+int devis_dcn_igemm_pack_weight(const void *weight, void *packed, int channels, int out_channels, int kernel_h, int kernel_w,
+                                void *stream)
+{
+    if (kernel_h <= 0 || kernel_w <= 0 || channels <= 0 || out_channels <= 0) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    const IgPlan p = igemm_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    if (!p.ok) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    if (!weight || !packed) return DEVIS_MSDA_ERR_NULL_POINTER;
+    const long long total = (long long)kernel_h * kernel_w * p.nchunks * p.Npad * devis::kIgBK;
+    const long long want = (total + 255) / 256;
+    const unsigned blocks = (unsigned)(want > devis_capi_helper_blocks() ? devis_capi_helper_blocks() : want);
+    devis::dcn_igemm_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float *)weight, (float *)packed, out_channels,
+                                                                          channels, kernel_h * kernel_w, p.Npad, p.nchunks);
+    return devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN);
+}
+
+int devis_dcn_igemm_forward(const void *input, const void *offset, const void *mask, const void *packed_weight,
+                            const void *bias, void *out, int batch, int height, int width, int channels, int out_h,
+                            int out_w, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                            int dil_h, int dil_w, int out_channels, int precision, void *stream)
+{
+    const DcnDims d{batch, height, width, channels, out_h, out_w, kernel_h, kernel_w,
+                    stride_h, stride_w, pad_h, pad_w, dil_h, dil_w};
+    const int rc = check_dims(d, DEVIS_MSDA_F32);
+    if (rc) return rc;
+    if (precision != DEVIS_DCN_PRECISION_3XTF32 && precision != DEVIS_DCN_PRECISION_TF32) return DEVIS_MSDA_ERR_BAD_SHAPE;
+    const IgPlan p = igemm_plan(channels, out_channels, kernel_h, kernel_w, DEVIS_MSDA_F32);
+    if (!p.ok) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    const long long P = (long long)batch * out_h * out_w;
+    if (P == 0) return DEVIS_MSDA_OK;
+    if (!input || !offset || !packed_weight || !out) return DEVIS_MSDA_ERR_NULL_POINTER;
+    // the producers address the input with 32-bit element offsets
+    if ((long long)batch * height * width * channels >= (1LL << 31) || (long long)out_h * out_w >= (1LL << 30) ||
+        (P + devis::kIgBM - 1) / devis::kIgBM > 0x7fffffffLL)
+        return DEVIS_MSDA_ERR_TOO_LARGE;
+    const int split = precision == DEVIS_DCN_PRECISION_3XTF32 ? 1 : 0;
+    devis::IgArgs a{};
+    a.input = (const float *)input;
+    a.offset = (const float *)offset;
+    a.mask = (const float *)mask;
+    a.wpacked = (const float *)packed_weight;
+    a.bias = (const float *)bias;
+    a.out = (float *)out;
+    a.d = d;
+    a.Cout = out_channels;
+    a.Npad = p.Npad;
+    a.nchunks = p.nchunks;
+    a.stages = p.stages(split);
+    a.split = split;
+    a.n0 = p.n0;
+    a.n1 = p.n1;
+    a.tmem_cols = p.tmem_cols;
+    a.P = P;
+    const size_t smem = p.smem(split);
+    const cudaError_t e = cudaFuncSetAttribute(devis::dcn_igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+    const unsigned grid = (unsigned)((P + devis::kIgBM - 1) / devis::kIgBM);
+    devis::dcn_igemm_fwd_kernel<<<grid, devis::kIgThreads, smem, (cudaStream_t)stream>>>(a);
+    return devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN_IGEMM);
 }
 
 }  // extern "C"

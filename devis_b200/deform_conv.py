@@ -265,6 +265,109 @@ class DeformConv2dFunction(Function):
         return grad_in, grad_off, grad_w, grad_b, grad_m, None, None, None
 
 
+_TENSOR_CORE = True
+
+
+def set_tensor_core(enabled):
+    """enable / disable the tcgen05 implicit-GEMM forward of the wide layers (default on); returns the previous setting"""
+    global _TENSOR_CORE
+    old, _TENSOR_CORE = _TENSOR_CORE, bool(enabled)
+    return old
+
+
+def _igemm_supported(c, cout, kh, kw, dtype):
+    if not _TENSOR_CORE or dtype != torch.float32:
+        return False
+    return bool(_lib.load().devis_dcn_igemm_supported(c, cout, kh, kw, _lib.F32))
+
+
+class IGemmDeformConv2dFunction(Function):
+    """apply(input, offset, weight, bias, mask, stride, padding, dilation) -> (N, Cout, Ho, Wo)
+
+    Forward of the wide mask-head layers as an implicit GEMM on the tensor cores (devis_dcn_igemm_forward, tcgen05 /
+    TMEM): no column matrix is written or kept.  Precision follows ``torch.backends.cuda.matmul.allow_tf32`` exactly as
+    torchvision's ``addmm`` would: off (the default) -> 3xTF32, fp32-grade; on -> one TF32 pass.  The backward is the
+    im2col form's (cuBLAS GEMMs + devis_dcn_col2im), with the columns RECOMPUTED for the weight gradient, so nothing of
+    column size lives between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, bias, mask, stride, padding, dilation):
+        n, c, h, w = input.shape
+        cout, _, kh, kw = weight.shape
+        (sh, sw), (ph, pw), (dh, dw) = stride, padding, dilation
+        ho, wo = _out_size(h, kh, sh, ph, dh), _out_size(w, kw, sw, pw, dw)
+        x = input.permute(0, 2, 3, 1)
+        x = x if x.is_contiguous() else x.contiguous()
+        offset = offset if offset.is_contiguous() else offset.contiguous()
+        if mask is not None:
+            mask = mask if mask.is_contiguous() else mask.contiguous()
+        if bias is not None:
+            bias = bias if bias.is_contiguous() else bias.contiguous()
+        lib = _lib.load()
+        wd = weight.detach()
+        wd = wd if wd.is_contiguous() else wd.contiguous()
+        packed = torch.empty(int(lib.devis_dcn_igemm_packed_weight_elems(c, cout, kh, kw)), dtype=torch.float32,
+                             device=input.device)
+        out = torch.empty((n, ho, wo, cout), dtype=input.dtype, device=input.device)
+        dims = (n, h, w, c, ho, wo, kh, kw, sh, sw, ph, pw, dh, dw)
+        precision = _lib.DCN_PRECISION_TF32 if torch.backends.cuda.matmul.allow_tf32 else _lib.DCN_PRECISION_3XTF32
+        with torch.cuda.device(input.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(lib.devis_dcn_igemm_pack_weight(_ptr(wd), _ptr(packed), c, cout, kh, kw, stream))
+            _lib.check(lib.devis_dcn_igemm_forward(_ptr(x), _ptr(offset), _ptr(mask), _ptr(packed), _ptr(bias), _ptr(out),
+                                                   *dims, cout, precision, stream))
+        ctx.dims, ctx.has_bias = dims, bias is not None
+        ctx.save_for_backward(x, offset, mask, wd)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, offset, mask, weight = ctx.saved_tensors
+        n, h, w, c, ho, wo, kh, kw = ctx.dims[:8]
+        cout, k = weight.shape[0], kh * kw
+        g2 = grad_out.permute(0, 2, 3, 1).reshape(n * ho * wo, cout)
+        g2 = g2 if g2.is_contiguous() else g2.contiguous()
+        w2 = weight.permute(0, 2, 3, 1).reshape(cout, k * c)
+        need_in, need_off, need_w, need_b, need_m = ctx.needs_input_grad[:5]
+        grad_w = grad_b = grad_in = grad_off = grad_m = None
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            if need_w:
+                per = max(1, min(n, _COLS_CHUNK_BYTES // max(1, ho * wo * k * c * 4)))
+                cols = torch.empty((per * ho * wo, k * c), dtype=x.dtype, device=x.device)
+                gw2 = torch.zeros((cout, k * c), dtype=x.dtype, device=x.device)
+                for n0 in range(0, n, per):
+                    n1 = min(n, n0 + per)
+                    rows = (n1 - n0) * ho * wo
+                    _lib.check(lib.devis_dcn_im2col(_ptr(x[n0:n1]), _ptr(offset[n0:n1]),
+                                                    _ptr(mask[n0:n1]) if mask is not None else None, _ptr(cols),
+                                                    n1 - n0, *ctx.dims[1:], _DTYPES[x.dtype], stream))
+                    gw2 += _wgrad(g2[n0 * ho * wo:n1 * ho * wo], cols[:rows])
+                del cols
+                grad_w = gw2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
+            if need_b and ctx.has_bias:
+                grad_b = g2.sum(0)
+            if need_in or need_off or (need_m and mask is not None):
+                if need_in:
+                    _alert_not_deterministic()
+                gx = torch.empty_like(x) if need_in else None
+                grad_off = torch.empty_like(offset)
+                grad_m = torch.empty_like(mask) if mask is not None else None
+                per = max(1, min(n, _COLS_CHUNK_BYTES // max(1, ho * wo * k * c * 4)))
+                for n0 in range(0, n, per):
+                    n1 = min(n, n0 + per)
+                    grad_cols = g2[n0 * ho * wo:n1 * ho * wo] @ w2
+                    _lib.check(lib.devis_dcn_col2im(_ptr(x[n0:n1]), _ptr(offset[n0:n1]),
+                                                    _ptr(mask[n0:n1]) if mask is not None else None, _ptr(grad_cols),
+                                                    _ptr(gx[n0:n1]) if need_in else None, _ptr(grad_off[n0:n1]),
+                                                    _ptr(grad_m[n0:n1]) if mask is not None else None, n1 - n0,
+                                                    *ctx.dims[1:], _DTYPES[x.dtype], stream))
+                grad_in = gx.permute(0, 3, 1, 2) if need_in else None
+        return grad_in, grad_off, grad_w, grad_b, grad_m, None, None, None
+
+
 def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None):
     """torchvision.ops.deform_conv2d (torchvision/ops/deform_conv.py:14), same arguments and result."""
     stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
@@ -301,5 +404,8 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     form = _fused_form(c, cout, kh, kw, input.dtype) if n > 0 else 0
     needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (input, offset, weight, bias, mask))
     fn = FusedDeformConv2dFunction if form & 1 and (form & 2 or not needs_grad) else DeformConv2dFunction
+    # wide layers (not served by the fused CUDA-core forms): forward on the tensor cores
+    if fn is DeformConv2dFunction and not form & 1 and n > 0 and _igemm_supported(c, cout, kh, kw, input.dtype):
+        fn = IGemmDeformConv2dFunction
     out = fn.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
     return out if out.dtype == out_dtype else out.to(out_dtype)

@@ -86,6 +86,28 @@ int devis_dcn_weight_grad(const void *input_nhwc, const void *offset, const void
                           int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
                           int dil_w, int out_channels, void *stream);
 
+/* ---- tensor-core form: the forward of the WIDE layers as an implicit GEMM on tcgen05 (dcn_igemm.cuh) -------------------
+ * Replaces deformable_im2col + at::addmm (torchvision/csrc/ops/cuda/deform_conv2d_kernel.cu, forward) for float32 layers
+ * with channels % 8 == 0, out_channels % 4 == 0 and out_channels <= 512 -- in DeVIS's mask head the 264 -> 264,
+ * 264 -> 128 and 136 -> 64 layers (deformable_segmentation.py:323-380), whose contraction dominates and which round 1 ran
+ * as im2col + cuBLAS fp32.  No column matrix: a thread block gathers and interpolates 128 output pixels x 32 channels
+ * at a time into shared memory, the weights stream in pre-packed, tcgen05.mma.kind::tf32 accumulates in tensor memory.
+ *   precision  DEVIS_DCN_PRECISION_3XTF32 (default): operands split hi + lo, three TF32 products per term, fp32-grade
+ *              result (<= 1e-5 against the float64 fixtures); DEVIS_DCN_PRECISION_TF32: one TF32 pass, for callers that
+ *              have torch.backends.cuda.matmul.allow_tf32 on (torchvision's addmm honours that switch as well).
+ * devis_dcn_igemm_pack_weight: torchvision's weight (out_channels, channels, kh, kw) -> the kernel's swizzled hi / lo
+ * slabs (devis_dcn_igemm_packed_weight_elems floats).  out: (N, Ho, Wo, out_channels) channels-last, fully written. */
+#define DEVIS_DCN_PRECISION_3XTF32 0
+#define DEVIS_DCN_PRECISION_TF32 1
+int devis_dcn_igemm_supported(int channels, int out_channels, int kernel_h, int kernel_w, int dtype);
+size_t devis_dcn_igemm_packed_weight_elems(int channels, int out_channels, int kernel_h, int kernel_w);
+int devis_dcn_igemm_pack_weight(const void *weight_oihw, void *packed, int channels, int out_channels, int kernel_h,
+                                int kernel_w, void *stream);
+int devis_dcn_igemm_forward(const void *input_nhwc, const void *offset, const void *mask, const void *packed_weight,
+                            const void *bias, void *out_nhwc, int batch, int height, int width, int channels, int out_h,
+                            int out_w, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                            int dil_h, int dil_w, int out_channels, int precision, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,8 +78,9 @@ uint64_t devis_msda_launch_count(void);
 #define DEVIS_MSDA_KERNEL_FUSED_BWD 5     /* tmsda_fused_bwd */
 #define DEVIS_MSDA_KERNEL_BWD_SORTED 6    /* msda_bwds (deterministic, encoder form) */
 #define DEVIS_MSDA_KERNEL_AUX 7           /* absmax / fixed-point finalize helpers */
-#define DEVIS_MSDA_KERNEL_DCN 8           /* include/devis_deform_conv.h kernels */
-#define DEVIS_MSDA_KERNEL_FAMILIES 9
+#define DEVIS_MSDA_KERNEL_DCN 8           /* include/devis_deform_conv.h kernels (CUDA-core forms, helpers) */
+#define DEVIS_MSDA_KERNEL_DCN_IGEMM 9     /* dcn_igemm_fwd (tcgen05 implicit GEMM) */
+#define DEVIS_MSDA_KERNEL_FAMILIES 10
 uint64_t devis_msda_kernel_launches(int family);
 /* Developer knobs of the benchmarks (launch shapes, kernel A/B selection).  They are inert in a product process:
  * unless the process was started with the environment variable DEVIS_MSDA_TUNING=1 this returns

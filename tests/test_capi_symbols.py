@@ -89,7 +89,7 @@ def test_argument_validation_happens_before_any_cuda_call():
     # per-family launch counters exist for every family the header names and nothing has been launched
     header = open(HEADER).read()
     n_fam = int(re.search(r"#define DEVIS_MSDA_KERNEL_FAMILIES (\d+)", header).group(1))
-    assert n_fam == 9 and all(lib.devis_msda_kernel_launches(f) == 0 for f in range(n_fam))
+    assert n_fam == 10 and all(lib.devis_msda_kernel_launches(f) == 0 for f in range(n_fam))
     assert lib.devis_msda_kernel_launches(-1) == 0 and lib.devis_msda_kernel_launches(n_fam) == 0
     for name in ("TREF_LEVEL0", "TREF_OWN", "TREF_SAMPLED"):
         assert re.search(rf"#define DEVIS_TMSDA_{name} {getattr(_lib, name)}\b", header)
