@@ -78,6 +78,17 @@ int devis_capi_check_launch(int family)
     return e == cudaSuccess ? DEVIS_MSDA_OK : devis_capi_cuda_fail(e);
 }
 
+#ifndef DEVIS_FWD_VIRTUAL
+#define DEVIS_FWD_VIRTUAL 1
+#endif
+// compile-time A/B of the launch shape of msda_fwdv_kernel (benchmarks/build_variants.py); 0 = pick_shape decides
+#ifndef DEVIS_FWDV_THREADS
+#define DEVIS_FWDV_THREADS 0
+#endif
+#ifndef DEVIS_FWDV_QPG
+#define DEVIS_FWDV_QPG 0
+#endif
+
 namespace {
 
 int cuda_fail(cudaError_t e) { return devis_capi_cuda_fail(e); }
@@ -167,13 +178,41 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     bool compact = lpg == 8 && (compact_mode == 1 || (compact_mode == 0 && dtype == DEVIS_MSDA_F32));
     for (int sg = 0; sg < a.n_seg; ++sg) compact = compact && (a.seg[sg].P % 4 == 0);
     if (compact) {
-        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32,
-                                         dtype == DEVIS_MSDA_BF16 ? 2 : 4, 0, 1);
+        LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32,
+                                   dtype == DEVIS_MSDA_BF16 ? 2 : 4, 0, 1);
+#if DEVIS_FWD_VIRTUAL
+        if (DEVIS_FWDV_THREADS && s.threads > DEVIS_FWDV_THREADS) s.threads = DEVIS_FWDV_THREADS;
+        if (DEVIS_FWDV_QPG && s.qpg > DEVIS_FWDV_QPG) s.qpg = DEVIS_FWDV_QPG;
+        if (s.threads > DEVIS_FWDV_MAXT) s.threads = DEVIS_FWDV_MAXT;
+#endif
         smem += (size_t)(s.threads / 32) * Tap16x8::kBytesPerWarp;
         const int qc = s.threads / 8;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
         if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
         const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
+#if DEVIS_FWD_VIRTUAL
+        // round 2: dead corners skipped, virtual top-left addressing (msda_fwdv_kernel); signed offsets -> value < 2 GiB
+        if ((unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31)) {
+#define DEVIS_FWDV(BF, QPG)                                                                                \
+    do {                                                                                                   \
+        if (d.M == 8) msda_fwdv_kernel<BF, QPG, SlotSrc, (BF ? 512 : 1024)><<<grid, s.threads, smem, st>>>(a); \
+        else msda_fwdv_kernel<BF, QPG, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);                      \
+    } while (0)
+            if (dtype == DEVIS_MSDA_BF16) {
+                if (s.qpg == 2) DEVIS_FWDV(true, 2);
+                else DEVIS_FWDV(true, 1);
+            } else {
+#if !DEVIS_FWDV_PREFETCH
+                if (s.qpg == 4) DEVIS_FWDV(false, 4);
+                else
+#endif
+                if (s.qpg >= 2) DEVIS_FWDV(false, 2);
+                else DEVIS_FWDV(false, 1);
+            }
+#undef DEVIS_FWDV
+            return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
+        }
+#endif
         if (dtype == DEVIS_MSDA_BF16) {
             if (s.qpg == 2) msda_fwdc_kernel<true, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
             else msda_fwdc_kernel<true, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
@@ -684,14 +723,30 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
     dim3 grid;
     int threads;
     size_t smem;
+    // round 2: dead corners skipped, virtual top-left addressing (signed 32-bit offsets: value < 2 GiB; 8 heads: the row
+    // size is a compile-time constant); DEVIS_FWD_VIRTUAL=0 builds keep the round-1 consumer
+    const bool virt = DEVIS_FWD_VIRTUAL && (unsigned long long)num_frames * spatial_size * num_heads * channels *
+                                                   elem_size(dtype) < (1ull << 31);
+#define DEVIS_FUSED_FWD(QPG, GEN)                                                                                          \
+    do {                                                                                                                   \
+        cudaStream_t st_ = (cudaStream_t)stream;                                                                           \
+        if (dtype == DEVIS_MSDA_BF16) {                                                                                    \
+            if (virt && num_heads == 8) tmsda_fused_fwd_kernel<true, QPG, GEN, 512><<<grid, threads, smem, st_>>>(a);      \
+            else if (virt) tmsda_fused_fwd_kernel<true, QPG, GEN, 0><<<grid, threads, smem, st_>>>(a);                     \
+            else tmsda_fused_fwd_kernel<true, QPG, GEN, -1><<<grid, threads, smem, st_>>>(a);                              \
+        } else {                                                                                                           \
+            if (virt && num_heads == 8) tmsda_fused_fwd_kernel<false, QPG, GEN, 1024><<<grid, threads, smem, st_>>>(a);    \
+            else if (virt) tmsda_fused_fwd_kernel<false, QPG, GEN, 0><<<grid, threads, smem, st_>>>(a);                    \
+            else tmsda_fused_fwd_kernel<false, QPG, GEN, -1><<<grid, threads, smem, st_>>>(a);                             \
+        }                                                                                                                  \
+    } while (0)
     // the general (decoder) form: boxes, per-level / instance-aware temporal reference points, by-products
     const bool general = ref_dim == 4 || (a.n_seg > 1 && temporal_ref_mode != 0) || loc_curr_out || aw_curr_out ||
                          a.loc_out[1] || a.aw_out[1];
     if (general) {
         rc = fused_grid(a, 0, grid, threads, smem, 1);
         if (rc) return rc;
-        if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd_kernel<true, 1, true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        else tmsda_fused_fwd_kernel<false, 1, true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        DEVIS_FUSED_FWD(1, true);
         return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
     }
     // bf16 value: four lanes x 8 channels per (query, head) like msda_fwd8_kernel (tuning key 4: 1 never, 2 always)
@@ -713,13 +768,9 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
     if (qpg != 1 && qpg != 2) qpg = (dtype == DEVIS_MSDA_F32 && num_query >= 2048) ? 2 : 1;
     rc = fused_grid(a, 0, grid, threads, smem, qpg);
     if (rc) return rc;
-    if (dtype == DEVIS_MSDA_BF16) {
-        if (qpg == 2) tmsda_fused_fwd_kernel<true, 2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        else tmsda_fused_fwd_kernel<true, 1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-    } else {
-        if (qpg == 2) tmsda_fused_fwd_kernel<false, 2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        else tmsda_fused_fwd_kernel<false, 1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-    }
+    if (qpg == 2) DEVIS_FUSED_FWD(2, false);
+    else DEVIS_FUSED_FWD(1, false);
+#undef DEVIS_FUSED_FWD
     return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
 }
 

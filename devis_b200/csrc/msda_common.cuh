@@ -140,6 +140,41 @@ __device__ __forceinline__ TapGeom tap_geometry(float x, float y, const int4 slo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Round 2: tap geometry with a VIRTUAL top-left corner.  In the DeVIS-like workload 28 % of all corners are dead (the
+// tap leaves a coarse map, or one row / column of its 2 x 2 footprint does): the reference never loads those
+// (cuh:56-78), and neither do the round-2 consumers -- every gathered row is a wavefront of the L1 data pipe, the
+// resource the kernels are bound by.  Dead corners are predicated off, so nothing needs clamping: the record carries the
+// byte offset of the footprint's top-left cell even when that cell is outside the map (row / column -1), the other
+// three addresses are TL + one value row, TL + one map row, TL + both, and four live bits say which of them exist.
+// ---------------------------------------------------------------------------------------------
+struct TapGeomV {
+    float lh, lw, hh, hw;   // fractional parts and complements
+    int rowv;               // value row of the (possibly virtual) top-left cell; may be up to W + 1 rows before the map
+    unsigned live;          // bit0 TL, bit1 TR, bit2 BL, bit3 BR inside the map; 0 if the tap fails the range test
+    unsigned ok;            // as TapGeom::ok
+};
+
+__device__ __forceinline__ TapGeomV tap_geometry_v(float x, float y, const int4 slot, bool live)
+{
+    TapGeomV g;
+    const int H = slot.x, W = slot.y;
+    const float h_im = __fadd_rn(__fmul_rn(y, (float)H), -0.5f);
+    const float w_im = __fadd_rn(__fmul_rn(x, (float)W), -0.5f);
+    const bool inb = live && h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int h0 = inb ? (int)hf : 0, w0 = inb ? (int)wf : 0;
+    g.lh = h_im - hf;
+    g.lw = w_im - wf;
+    g.hh = 1.f - g.lh;
+    g.hw = 1.f - g.lw;
+    const unsigned top = h0 >= 0, bot = h0 + 1 <= H - 1, left = w0 >= 0, right = w0 + 1 <= W - 1;
+    g.ok = inb ? (top | (bot << 1) | (left << 2) | (right << 3)) : 0u;
+    g.live = inb ? ((top & left) | ((top & right) << 1) | ((bot & left) << 2) | ((bot & right) << 3)) : 0u;
+    g.rowv = slot.z + h0 * W + w0;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tap exchange through shared memory.  A group of LPG lanes owns one (query, head); lane j prepares
 // tap k0+j and publishes a 32-byte record; then all lanes of the group walk the LPG records.
 // (Round-1 profile: doing this with __shfl_sync cost 6 L1-data-pipe wavefronts per tap -- shuffles

@@ -323,6 +323,251 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
 }
 
 // =================================================================================================
+// msda_fwdv_kernel (round 2) -- msda_fwdc_kernel with DEAD CORNERS SKIPPED and a cheaper consumer.
+//   record = { signed byte offset of the footprint's top-left cell | 4 live bits,  w*hh,  w*lh,  lw }
+// (tap_geometry_v).  The consumer forms TL = base + offset and BL = TL + map-row pitch (two 64-bit adds); TR and BR are
+// the same two registers with an IMMEDIATE of one value row when the row size is a compile-time constant (ROWB: 8 heads
+// x 32 channels = 1024 B fp32 / 512 B bf16 -- every DeVIS configuration), so a tap costs 4 address instructions
+// instead of 8 and none of the clamp / mask selects of decode_tap16.  The four gathers and their 16 FFMA are predicated
+// on the live bits: a corner outside its map costs no L1 wavefront (28 % of all corners at the DeVIS layer-clip, where
+// most taps into the 6 x 10 and 12 x 20 maps of the other frames leave the map) and, unlike the zero-factor form, can
+// not leak a non-finite value of a neighbouring pixel into the result.  Offsets are signed 32-bit: value < 2 GiB.
+// =================================================================================================
+#ifndef DEVIS_FWDV_MIN_BLOCKS
+#define DEVIS_FWDV_MIN_BLOCKS 2
+#endif
+#ifndef DEVIS_FWDV_MAXT
+#define DEVIS_FWDV_MAXT 256
+#endif
+#ifndef DEVIS_FWDV_PREFETCH
+#define DEVIS_FWDV_PREFETCH 0
+#endif
+#ifndef DEVIS_FWDV_TB
+#define DEVIS_FWDV_TB 2
+#endif
+// Predicated gather / accumulate as straight-line PTX: written as C++ `if (live) v = load; ... if (live) acc += c * v;`
+// the front end merges the two regions and the load is followed at once by its first use -- one gather in flight per
+// warp.  As PTX the eight gathers of a tap pair are issued back to back like the unpredicated ones of msda_fwdc_kernel.
+// A predicated-off gather keeps the previous content of its destination ("+f": ptxas treats a predicated write as a
+// read-modify-write anyway, and with write-only operands it kept all 128 destinations of an exchange live from kernel
+// entry -- 1.4 KB of spills); the 32 destination registers therefore live in the kernel's scope, zeroed once.  Only the
+// equally predicated FFMAs read them.
+__device__ __forceinline__ void ldg_f4_if(float4 &v, const char *p, unsigned live)
+{
+#if DEVIS_HINTS & 4
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+#endif
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(p), "r"(live));
+}
+// four consecutive bf16 channels, widened (bf16 -> fp32 is a shift, so the conversion needs no predicate)
+__device__ __forceinline__ void ldg_bf16x4_if(float4 &v, const char *p, unsigned live)
+{
+    unsigned lo = __float_as_uint(v.x), hi = __float_as_uint(v.z);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0,%1}, [%2];\n\t}" : "+r"(lo), "+r"(hi) : "l"(p), "r"(live));
+    v.x = __uint_as_float(lo << 16);
+    v.y = __uint_as_float(lo & 0xffff0000u);
+    v.z = __uint_as_float(hi << 16);
+    v.w = __uint_as_float(hi & 0xffff0000u);
+}
+#ifndef DEVIS_FWDV_FFMA2
+#define DEVIS_FWDV_FFMA2 0
+#endif
+__device__ __forceinline__ void fma4_if(float4 &acc, float c, const float4 &v, unsigned live)
+{
+#if DEVIS_FWDV_FFMA2
+    // packed fp32 pairs (fma.rn.f32x2, new on sm_100): two instructions per corner instead of four
+    asm("{\n\t.reg .pred p;\n\t.reg .b64 cc, v01, v23, a01, a23;\n\tsetp.ne.u32 p, %9, 0;\n\t"
+        "mov.b64 cc, {%4, %4};\n\tmov.b64 v01, {%5, %6};\n\tmov.b64 v23, {%7, %8};\n\t"
+        "mov.b64 a01, {%0, %1};\n\tmov.b64 a23, {%2, %3};\n\t"
+        "@p fma.rn.f32x2 a01, cc, v01, a01;\n\t@p fma.rn.f32x2 a23, cc, v23, a23;\n\t"
+        "mov.b64 {%0, %1}, a01;\n\tmov.b64 {%2, %3}, a23;\n\t}"
+        : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+        : "f"(c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(live));
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
+        "@p fma.rn.f32 %0, %4, %5, %0;\n\t@p fma.rn.f32 %1, %4, %6, %1;\n\t@p fma.rn.f32 %2, %4, %7, %2;\n\t@p fma.rn.f32 %3, %4, %8, %3;\n\t}"
+        : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+        : "f"(c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(live));
+#endif
+}
+
+template <bool BF16, int ROWB>
+__device__ __forceinline__ void consume_tap16v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch_lo,
+                                               unsigned pitch_hi, const char *vbase, float4 &acc,
+                                               float4 (&v)[DEVIS_FWDV_TB][4])
+{
+    constexpr int TB = DEVIS_FWDV_TB;       // taps whose gathers are in flight together
+    const unsigned rowb = ROWB ? (unsigned)ROWB : rowbytes_rt;
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += TB) {
+        const char *pt[TB], *pb[TB];
+        float c[TB][4];
+        unsigned flags[TB];
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16x8::word(j0 + u, g));
+            flags[u] = r.x;
+            pt[u] = vbase + (ptrdiff_t)(int)(r.x & ~15u);
+            pb[u] = pt[u] + ((j0 + u) < 4 ? pitch_lo : pitch_hi);
+            const float lw = __uint_as_float(r.w), hw = 1.f - lw;
+            const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
+            c[u][0] = whh * hw;
+            c[u][1] = whh * lw;
+            c[u][2] = wlh * hw;
+            c[u][3] = wlh * lw;
+        }
+#pragma unroll
+        for (int u = 0; u < TB; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const char *addr = ((e & 2) ? pb[u] : pt[u]) + ((e & 1) ? rowb : 0u);
+                if (BF16) ldg_bf16x4_if(v[u][e], addr, flags[u] & (1u << e));
+                else ldg_f4_if(v[u][e], addr, flags[u] & (1u << e));
+            }
+#pragma unroll
+        for (int u = 0; u < TB; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) fma4_if(acc, c[u][e], v[u][e], flags[u] & (1u << e));
+    }
+}
+
+__device__ __forceinline__ uint4 make_tap16v(const TapGeomV &t, float w, unsigned rowbytes)
+{
+    uint4 rec;
+    rec.x = (unsigned)(t.rowv * (int)rowbytes) | t.live;
+    rec.y = __float_as_uint(w * t.hh);
+    rec.z = __float_as_uint(w * t.lh);
+    rec.w = __float_as_uint(t.lw);
+    return rec;
+}
+
+template <bool BF16, int QPG, class SlotSrc, int ROWB>
+__global__ void __launch_bounds__(DEVIS_FWDV_MAXT, DEVIS_FWDV_MIN_BLOCKS) msda_fwdv_kernel(const FwdArgs<SlotSrc> a)
+{
+    constexpr int LPG = 8;
+    extern __shared__ int4 s_slot[];
+    const int outer = blockIdx.y;
+    build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16x8::kWordsPerWarpBuf);
+
+    const int M = a.d.M, Lq = a.d.Lq;
+    const int j = threadIdx.x & 7, g = (threadIdx.x & 31) >> 3, grp = threadIdx.x >> 3, QC = blockDim.x >> 3;
+    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+
+    int q[QPG];
+    bool qlive[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        const int qi = (qchunk * QPG + i) * QC + grp;
+        qlive[i] = qi < Lq;
+        q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
+    }
+
+    constexpr unsigned kQuadBytes = BF16 ? 8u : 16u;
+    const unsigned rowbytes = ROWB ? (unsigned)ROWB : (unsigned)(M * LPG) * kQuadBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
+    asm volatile("" : "+l"(vbase));
+
+    float4 acc[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    struct TapIn {
+        float2 xy;
+        float w;
+    };
+    auto load_taps = [&](int sg, int k0, TapIn (&in)[QPG]) {
+        const int K = a.seg[sg].n_slots * a.seg[sg].P;
+        const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
+        const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
+        const int k = k0 + j;
+#pragma unroll
+        for (int i = 0; i < QPG; ++i) {
+            const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+            in[i].xy = make_float2(0.f, 0.f);
+            in[i].w = 0.f;
+            if (k < K && qlive[i]) {
+                in[i].xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                in[i].w = ld_stream_f(aw + row * K + k);
+            }
+        }
+    };
+
+    float4 v[DEVIS_FWDV_TB][4];             // gather destinations (see ldg_f4_if)
+#pragma unroll
+    for (int u = 0; u < DEVIS_FWDV_TB; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[u][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int slot_base = 0, parity = 0;
+    TapIn nxt[QPG];
+    load_taps(0, 0, nxt);
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);   // P % 4 == 0, hence K % 4 == 0
+        for (int k0 = 0; k0 < K; k0 += LPG) {
+            const int k = k0 + j;
+            const bool klive = k < K;
+            const int4 sl = s_slot[slot_base + (klive ? div_p(k, P, pshift) : 0)];
+            const unsigned my_pitch = (unsigned)sl.y * rowbytes;
+            const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);   // slot of taps k0 .. k0+3
+            const unsigned pitch_hi = __shfl_sync(0xffffffffu, my_pitch, 4, 8);   // slot of taps k0+4 .. k0+7
+            TapIn cur[QPG];
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) cur[i] = nxt[i];
+            if (k0 + LPG < K) load_taps(sg, k0 + LPG, nxt);
+            else if (sg + 1 < a.n_seg) load_taps(sg + 1, 0, nxt);
+#if DEVIS_FWDV_PREFETCH
+            // EXPERIMENT: all QPG records are published first and the producing lane asks for its tap's live rows
+            // (prefetch.global.L1, no destination register, no scoreboard), so that the gathers of the later taps find
+            // their lines in L1 instead of waiting ~400 cycles for L2
+            static_assert(QPG <= 2, "two exchange buffers");
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) {
+                const TapGeomV t = tap_geometry_v(cur[i].xy.x, cur[i].xy.y, sl, klive && qlive[i]);
+                const uint4 rec = make_tap16v(t, cur[i].w, rowbytes);
+                *reinterpret_cast<uint4 *>(xbuf + i * Tap16x8::kWordsPerWarpBuf + Tap16x8::word(j, g)) = rec;
+                const char *pt = vbase + (ptrdiff_t)(int)(rec.x & ~15u);
+                const char *pb = pt + my_pitch;
+                if (rec.x & 1u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pt));
+                if (rec.x & 2u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pt + rowbytes));
+                if (rec.x & 4u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb));
+                if (rec.x & 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + rowbytes));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < QPG; ++i)
+                consume_tap16v<BF16, ROWB>(xbuf + i * Tap16x8::kWordsPerWarpBuf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
+            __syncwarp();
+#else
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) {
+                const TapGeomV t = tap_geometry_v(cur[i].xy.x, cur[i].xy.y, sl, klive && qlive[i]);
+                float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
+                parity ^= 1;
+                *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16v(t, cur[i].w, rowbytes);
+                __syncwarp();
+                consume_tap16v<BF16, ROWB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
+            }
+#endif
+        }
+        slot_base += a.seg[sg].n_slots;
+    }
+
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        if (!qlive[i]) continue;
+        const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+        if (BF16)
+            reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc[i]);
+        else
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row * LPG + j, acc[i]);
+    }
+}
+
+// =================================================================================================
 // msda_fwd8_kernel -- D = 32 only: FOUR lanes per (query, head), 8 channels per lane.
 //
 // Round-1b profile + benchmarks/micro/l1_patterns.cu: the forward is bound by the SM's L1/shared data

@@ -182,8 +182,13 @@ __device__ __forceinline__ void raw_to_operands(const FusedArgs &a, int sg, cons
     w = expf(r.lg - rmax) * rinv;
 }
 
-template <bool BF16, int QPG, bool GEN = false>
-__global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs a)
+// ROWB: -1 = clamped corners with zero factors (round 1); >= 0 = dead corners skipped, virtual top-left addressing
+// (consume_tap16v, msda_fwd.cuh; 0: row size at run time, else bytes of one value row)
+#ifndef DEVIS_FUSED_FWD_MIN_BLOCKS
+#define DEVIS_FUSED_FWD_MIN_BLOCKS 2
+#endif
+template <bool BF16, int QPG, bool GEN = false, int ROWB = -1>
+__global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 3) tmsda_fused_fwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
     extern __shared__ int4 s_slot[];
@@ -219,6 +224,12 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
         acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
+    float4 v[DEVIS_FWDV_TB][4];             // gather destinations of consume_tap16v (see ldg_f4_if)
+#pragma unroll
+    for (int u = 0; u < DEVIS_FWDV_TB; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[u][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+
     RawTap nxt[QPG];
 #pragma unroll
     for (int i = 0; i < QPG; ++i) nxt[i] = load_raw_tap<GEN>(a, 0, row[i], qrow[i], j, qlive[i]);
@@ -252,12 +263,19 @@ __global__ void __launch_bounds__(256, 3) tmsda_fused_fwd_kernel(const FusedArgs
                     if (a.loc_out[sg]) reinterpret_cast<float2 *>(a.loc_out[sg] + row[i] * K * 2)[k] = make_float2(x, y);
                     if (a.aw_out[sg]) a.aw_out[sg][row[i] * K + k] = w;
                 }
-                const TapGeom t = tap_geometry(x, y, sl, live);
                 float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
                 parity ^= 1;
-                *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
-                __syncwarp();
-                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], pol);
+                if (ROWB >= 0) {
+                    const TapGeomV t = tap_geometry_v(x, y, sl, live);
+                    *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16v(t, w, rowbytes);
+                    __syncwarp();
+                    consume_tap16v<BF16, (ROWB > 0 ? ROWB : 0)>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
+                } else {
+                    const TapGeom t = tap_geometry(x, y, sl, live);
+                    *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
+                    __syncwarp();
+                    consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], pol);
+                }
             }
         }
         slot_base += a.n_slots[sg];

@@ -47,6 +47,17 @@ def _temporal_pyramid(spatial_shapes, n_slots):
     'temporal' half of the shape / start-index pairs (devis_transformer.py:97,118)."""
     shapes = spatial_shapes.repeat(n_slots, 1)
     lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    # the numbers are known on the host (pyramid_tensors attached them): hand them on, so that the modules' argument
+    # validation (clip_geometry.from_reference_args) never reads these tensors back from the device
+    host = getattr(spatial_shapes, clip_geometry._ATTR, None)
+    if host is not None and host[0] == spatial_shapes._version:
+        rows = [list(r) for r in host[1]] * n_slots
+        starts, acc = [], 0
+        for h, w in rows:
+            starts.append(acc)
+            acc += h * w
+        clip_geometry.attach_host_copy(shapes, rows)
+        clip_geometry.attach_host_copy(lsi, starts)
     return shapes, lsi
 
 

@@ -23,6 +23,8 @@ module's 5-tuple (lists of per-frame location tensors).  The kernels of this pac
 device tensor back once the clip geometry is memoised (clip_geometry.from_reference_args), which is what makes the
 capture possible; the warm-up calls that ``make_graphed_callables`` issues before capturing do that memoisation.
 """
+import gc
+
 import torch
 from torch import nn
 
@@ -81,9 +83,19 @@ class GraphedLayer(nn.Module):
         self.flat = _Flat(module, self.template, self.static_kwargs)
         samples = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in sample_args if _is_dynamic(a))
         # make_graphed_callables swaps the module's forward for the graphed one and returns the module
-        with torch.cuda.device(dev):
-            self.graphed = torch.cuda.make_graphed_callables(self.flat, samples, num_warmup_iters=num_warmup_iters,
-                                                             allow_unused_input=True)
+        # No cyclic garbage collection while the graphs are captured: a collection that happens to run mid-capture
+        # and frees an object owning CUDA resources (an older CUDA graph and its memory pool, for one) issues calls
+        # that invalidate every capture in progress ("operation failed due to a previous error during capture").
+        gc.collect()
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.device(dev):
+                self.graphed = torch.cuda.make_graphed_callables(self.flat, samples, num_warmup_iters=num_warmup_iters,
+                                                                 allow_unused_input=True)
+        finally:
+            if was_enabled:
+                gc.enable()
 
     @property
     def module(self):
