@@ -803,6 +803,29 @@ def run_ours(args, rank, world, local_rank):
             import traceback
             extra["train_trunk"] = {"error": str(exc)[:300], "where": traceback.format_exc()[-700:]}
 
+    # ---- BASELINE.json config 3: DeVIS R50 T=6 full-model inference (rank 0, one GPU's rate; benchmarks/devis_r50_inference.py)
+    if rank == 0 and not args.only_headline and dtype == torch.float32:
+        try:
+            torch.cuda.empty_cache()
+            from benchmarks import devis_r50_inference
+            full = {}
+            for mode in ("off", "on"):
+                r = devis_r50_inference.run("both", iters=10, breakdown=False, tf32=mode == "on")
+                full["tf32_" + mode] = {"ours_ms_per_clip": r.get("ours", {}).get("ms_per_clip_median"),
+                                        "ours_clips_per_sec": r.get("ours", {}).get("clips_per_sec"),
+                                        "reference_ops_ms_per_clip": r.get("reference_ops", {}).get("ms_per_clip_median"),
+                                        "speedup": r.get("speedup"), "config": r.get("config")}
+                if "error" in r.get("reference_ops", {}):
+                    full["tf32_" + mode]["reference_ops_error"] = r["reference_ops"]["error"]
+            full["what"] = ("whole model on one GPU: torchvision ResNet-50 + DeVIS transformer (6 + 6 layers) + box heads + top-k + "
+                            "mask head; 'reference_ops' = same weights with the reference's attention loop / CUDA op and "
+                            "torchvision's deform_conv2d")
+            extra["full_model_inference"] = full
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+        except Exception as exc:   # noqa: BLE001
+            extra["full_model_inference"] = {"error": str(exc)[:300]}
+
     if rank == 0:
         bwd_kernel = "msda_bwd_kernel"
         line = {

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
 // not leak a non-finite value of a neighbouring pixel into the result.  Offsets are signed 32-bit: value < 2 GiB.
 // =================================================================================================
 #ifndef DEVIS_FWDV_MIN_BLOCKS
-#define DEVIS_FWDV_MIN_BLOCKS 2
+#define DEVIS_FWDV_MIN_BLOCKS 3
 #endif
 #ifndef DEVIS_FWDV_MAXT
 #define DEVIS_FWDV_MAXT 256
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
 #define DEVIS_FWDV_PREFETCH 0
 #endif
 #ifndef DEVIS_FWDV_TB
-#define DEVIS_FWDV_TB 2
+#define DEVIS_FWDV_TB 1
 #endif
 // Predicated gather / accumulate as straight-line PTX: written as C++ `if (live) v = load; ... if (live) acc += c * v;`
 // the front end merges the two regions and the load is followed at once by its first use -- one gather in flight per
@@ -394,12 +394,11 @@ __device__ __forceinline__ void fma4_if(float4 &acc, float c, const float4 &v, u
 #endif
 }
 
-template <bool BF16, int ROWB>
+// TB = taps whose gathers are in flight together (v: their destinations, owned by the kernel)
+template <bool BF16, int ROWB, int TB>
 __device__ __forceinline__ void consume_tap16v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch_lo,
-                                               unsigned pitch_hi, const char *vbase, float4 &acc,
-                                               float4 (&v)[DEVIS_FWDV_TB][4])
+                                               unsigned pitch_hi, const char *vbase, float4 &acc, float4 (&v)[TB][4])
 {
-    constexpr int TB = DEVIS_FWDV_TB;       // taps whose gathers are in flight together
     const unsigned rowb = ROWB ? (unsigned)ROWB : rowbytes_rt;
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += TB) {
@@ -539,7 +538,7 @@ __global__ void __launch_bounds__(DEVIS_FWDV_MAXT, DEVIS_FWDV_MIN_BLOCKS) msda_f
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < QPG; ++i)
-                consume_tap16v<BF16, ROWB>(xbuf + i * Tap16x8::kWordsPerWarpBuf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
+                consume_tap16v<BF16, ROWB, DEVIS_FWDV_TB>(xbuf + i * Tap16x8::kWordsPerWarpBuf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
             __syncwarp();
 #else
 #pragma unroll
@@ -549,7 +548,7 @@ __global__ void __launch_bounds__(DEVIS_FWDV_MAXT, DEVIS_FWDV_MIN_BLOCKS) msda_f
                 parity ^= 1;
                 *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16v(t, cur[i].w, rowbytes);
                 __syncwarp();
-                consume_tap16v<BF16, ROWB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
+                consume_tap16v<BF16, ROWB, DEVIS_FWDV_TB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
             }
 #endif
         }

@@ -184,8 +184,13 @@ __device__ __forceinline__ void raw_to_operands(const FusedArgs &a, int sg, cons
 
 // ROWB: -1 = clamped corners with zero factors (round 1); >= 0 = dead corners skipped, virtual top-left addressing
 // (consume_tap16v, msda_fwd.cuh; 0: row size at run time, else bytes of one value row)
+// measured (round 2, fused-prologue forward at the DeVIS layer-clip): 2 taps in flight at 2 blocks per SM 580 us, 1 tap
+// at 2 / 3 blocks 605 / 595 us -- the opposite of msda_fwdv_kernel (1 tap, 3 blocks: 480 us against 489 us)
 #ifndef DEVIS_FUSED_FWD_MIN_BLOCKS
 #define DEVIS_FUSED_FWD_MIN_BLOCKS 2
+#endif
+#ifndef DEVIS_FUSED_FWD_TB
+#define DEVIS_FUSED_FWD_TB 2
 #endif
 template <bool BF16, int QPG, bool GEN = false, int ROWB = -1>
 __global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 3) tmsda_fused_fwd_kernel(const FusedArgs a)
@@ -224,9 +229,9 @@ __global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 
         acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    float4 v[DEVIS_FWDV_TB][4];             // gather destinations of consume_tap16v (see ldg_f4_if)
+    float4 v[DEVIS_FUSED_FWD_TB][4];        // gather destinations of consume_tap16v (see ldg_f4_if)
 #pragma unroll
-    for (int u = 0; u < DEVIS_FWDV_TB; ++u)
+    for (int u = 0; u < DEVIS_FUSED_FWD_TB; ++u)
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[u][e] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 
                     const TapGeomV t = tap_geometry_v(x, y, sl, live);
                     *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16v(t, w, rowbytes);
                     __syncwarp();
-                    consume_tap16v<BF16, (ROWB > 0 ? ROWB : 0)>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
+                    consume_tap16v<BF16, (ROWB > 0 ? ROWB : 0), DEVIS_FUSED_FWD_TB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
                 } else {
                     const TapGeom t = tap_geometry(x, y, sl, live);
                     *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
