@@ -50,6 +50,14 @@ T_FRAMES, S_ROWS, HEADS, CH, K_TAPS = 6, 4820, 8, 32, 96
 CLIP_NAMES = ("value", "loc_curr", "aw_curr", "loc_temporal", "aw_temporal")
 
 
+def workload_config(dist, world, half_acc=False):
+    """`config` of the JSON line -- identical for the GPU arm and the reference arm of the same workload"""
+    return {"workload": WORKLOAD, "dist": dist, "taps": "boundary-safe",
+            "l2_policy": "inputs larger than L2 (326 MB of operands per step vs 126 MB L2); no flush",
+            "clips_per_rank_per_step": 1, "parallelism": f"clip-sharded x{world}, no collective",
+            "grad_value_accumulation": "bf16 (opt-in flag)" if half_acc else "f32"}
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -232,7 +240,7 @@ def run_reference(args, rank):
         "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": per_clip * 1e3,
         "ms_per_step_median": statistics.median(times) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "dist": args.dist},
+        "config": workload_config(args.dist, args.gpus),        # the SAME dictionary as the GPU arm's (the driver compares them)
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": job.cores, "kind": "port", "sample": job.SAMPLE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
@@ -832,10 +840,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "dist": args.dist, "taps": "boundary-safe",
-                       "l2_policy": "inputs larger than L2 (326 MB of operands per step vs 126 MB L2); no flush",
-                       "clips_per_rank_per_step": 1, "parallelism": f"clip-sharded x{world}, no collective",
-                       "grad_value_accumulation": "bf16 (opt-in flag)" if half_acc else "f32"},
+            "config": workload_config(args.dist, world, half_acc),
             "us_fwd": us_fwd, "us_bwd": us_bwd,
             "kernel_us": {"fwd": {k: round(v, 1) for k, v in k_fwd.items()}, "bwd": {k: round(v, 1) for k, v in k_bwd.items()},
                           "fwd_cold_l2": {k: round(v, 1) for k, v in c_fwd.items()},

@@ -99,3 +99,59 @@ def test_fuzz_whole_clip_vs_per_call(seed):
                 clip["value"][src][None], shp, lsi, clip["loc_temporal"][f][None, :, :, j * nl:(j + 1) * nl].contiguous(),
                 clip["aw_temporal"][f][None, :, :, j * nl:(j + 1) * nl].contiguous(), 64)
         assert nmax(out[f].cpu().numpy(), want[0].cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("m,p,seed", [(8, 4, 1), (8, 8, 2), (3, 4, 3), (1, 8, 4), (5, 4, 5), (8, 4, 6)])
+def test_dead_corner_forward_path_with_taps_leaving_tiny_maps(m, p, seed):
+    """The round-2 forward (msda_fwdv_kernel: D = 32, P % 4 == 0) predicates dead corners off and addresses the other three
+    from a VIRTUAL top-left cell.  Maps of one row / one column / one pixel with a third of the taps outside exercise every
+    combination of dead rows and columns, for 8 heads (row size as an immediate) and other head counts (run-time row size);
+    forward and all three gradients against the C oracle, bf16 value against the fp32 result."""
+    from devis_b200 import _lib, synthetic
+    from oracle import c_oracle
+    rng = np.random.default_rng(seed)
+    shapes = [(1, 1), (1, int(rng.integers(2, 9))), (int(rng.integers(2, 9)), 1), (2, 2), (int(rng.integers(3, 12)), int(rng.integers(3, 12)))]
+    n, lq, d = 2, 37, 32
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    s = sum(h * w for h, w in shapes)
+    sizes = torch.tensor([[w, h] for h, w in shapes], device="cuda", dtype=torch.float32)
+    loc = torch.rand(n, lq, m, len(shapes), p, 2, generator=g, device="cuda") * 1.6 - 0.3
+    loc = synthetic.make_boundary_safe(loc, sizes).contiguous()
+    aw = torch.softmax(torch.randn(n, lq, m, len(shapes) * p, generator=g, device="cuda"), -1).view(n, lq, m, len(shapes), p).contiguous()
+    value = torch.randn(n, s, m, d, generator=g, device="cuda")
+    gout = torch.randn(n, lq, m * d, generator=g, device="cuda")
+    shp = torch.tensor(shapes, device="cuda")
+    areas = shp[:, 0] * shp[:, 1]
+    lsi = torch.cat([areas.new_zeros(1), areas.cumsum(0)[:-1]])
+    before = _lib.kernel_launches(_lib.KERNEL_FWD_GROUPED)
+    got = _run(value, shp, lsi, loc, aw, gout)
+    assert _lib.kernel_launches(_lib.KERNEL_FWD_GROUPED) == before + 1      # the grouped-lane forward, not the generic one
+    args = [a.cpu().numpy() for a in (value, shp, lsi, loc, aw, gout)]
+    want = (c_oracle.forward(*args[:5]),) + c_oracle.backward(*args)
+    for a, w, tol in zip(got, want, (1e-5, 1e-4, 1e-4, 1e-4)):
+        assert nmax(a.cpu().numpy(), w) < tol
+    # bf16 value through the same kernel template (64-byte rows, row size 512 B as the immediate)
+    from devis_b200 import MSDeformAttnFunction
+    out_bf16 = MSDeformAttnFunction.apply(value.bfloat16(), shp, lsi, loc, aw, 64)
+    assert nmax(out_bf16.float().cpu().numpy(), got[0].cpu().numpy()) < 1e-2
+
+
+def test_out_of_range_taps_do_not_read_the_map():
+    """Reference semantics (cuh:285-288, 56-78): a tap outside the map, or a corner outside it, reads nothing.  Round 1
+    read a clamped in-map pixel with a zero factor, so a NaN / Inf there leaked into queries that never sample it; the
+    round-2 forward does not load dead corners at all."""
+    from devis_b200 import MSDeformAttnFunction
+    m, d, p = 8, 32, 4
+    shp = torch.tensor([[4, 4]], device="cuda")
+    lsi = torch.zeros(1, dtype=torch.long, device="cuda")
+    value = torch.randn(1, 16, m, d, device="cuda")
+    loc = torch.full((1, 5, m, 1, p, 2), 0.9, device="cuda")          # cell (3, 3): right column and bottom row are dead
+    loc[..., 0, :] = 1.5                                               # first point of every (query, head): out of range
+    aw = torch.full((1, 5, m, 1, p), 0.25, device="cuda")
+    clean = MSDeformAttnFunction.apply(value, shp, lsi, loc, aw, 64)
+    poisoned = value.clone()
+    poisoned[0, 0] = float("nan")                                      # pixel (0, 0): no live corner touches it
+    poisoned[0, 1] = float("inf")
+    out = MSDeformAttnFunction.apply(poisoned, shp, lsi, loc, aw, 64)
+    assert torch.isfinite(out).all()
+    assert torch.equal(out, clean)
