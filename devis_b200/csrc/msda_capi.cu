@@ -162,6 +162,19 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
         if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
         const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
 #define DEVIS_FWD8(BF, QPG) msda_fwd8_kernel<BF, QPG, SlotSrc><<<grid, s.threads, smem, st>>>(a)
+#if DEVIS_FWD_VIRTUAL
+        // round 2: bf16 value with the dead corners skipped (msda_fwd8v_kernel); signed offsets -> value < 2 GiB
+        if (dtype == DEVIS_MSDA_BF16 && (unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31)) {
+            if (d.M == 8) {
+                if (s.qpg == 2) msda_fwd8v_kernel<2, SlotSrc, 512><<<grid, s.threads, smem, st>>>(a);
+                else msda_fwd8v_kernel<1, SlotSrc, 512><<<grid, s.threads, smem, st>>>(a);
+            } else {
+                if (s.qpg == 2) msda_fwd8v_kernel<2, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);
+                else msda_fwd8v_kernel<1, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);
+            }
+            return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
+        }
+#endif
         if (dtype == DEVIS_MSDA_BF16) {
             if (s.qpg == 2) DEVIS_FWD8(true, 2);
             else DEVIS_FWD8(true, 1);
@@ -759,7 +772,11 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
         if (chunks * num_heads > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
         grid = dim3((unsigned)(chunks * num_heads), (unsigned)num_frames);
         smem = (size_t)(a.n_slots[0] + a.n_slots[1]) * sizeof(int4) + (size_t)(threads / 32) * Tap16::kBytesPerWarp;
-        if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd8_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        if (dtype == DEVIS_MSDA_BF16 && virt && num_heads == 8)
+            tmsda_fused_fwd8_kernel<true, 512><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else if (dtype == DEVIS_MSDA_BF16 && virt)
+            tmsda_fused_fwd8_kernel<true, 0><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd8_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
         else tmsda_fused_fwd8_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
         return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
     }

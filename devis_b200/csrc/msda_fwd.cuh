@@ -729,4 +729,127 @@ __global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a
     }
 }
 
+// =================================================================================================
+// msda_fwd8v_kernel (round 2) -- msda_fwd8_kernel for bf16 value with the dead corners skipped: the record and the
+// addressing of msda_fwdv_kernel (virtual top-left cell, live bits, row size as an immediate), four lanes x 8 channels per
+// (query, head), 16-byte gathers predicated on the live bits.  The bf16 forward is the kernel closest to the data-pipe
+// limit (87 % busy), so the 28 % of rows that need not be fetched show up in the time.
+// =================================================================================================
+__device__ __forceinline__ void ldg_u4_if(uint4 &v, const char *p, unsigned live)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
+        : "l"(p), "r"(live));
+}
+__device__ __forceinline__ void fma8_bf16_if(float (&acc)[8], float c, const uint4 &raw, unsigned live)
+{
+    // bf16 -> fp32 is a shift / mask; done unconditionally (cheap, no faults), only the FFMAs carry the predicate
+    const float v0 = __uint_as_float(raw.x << 16), v1 = __uint_as_float(raw.x & 0xffff0000u);
+    const float v2 = __uint_as_float(raw.y << 16), v3 = __uint_as_float(raw.y & 0xffff0000u);
+    const float v4 = __uint_as_float(raw.z << 16), v5 = __uint_as_float(raw.z & 0xffff0000u);
+    const float v6 = __uint_as_float(raw.w << 16), v7 = __uint_as_float(raw.w & 0xffff0000u);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %17, 0;\n\t"
+        "@p fma.rn.f32 %0, %8, %9, %0;\n\t@p fma.rn.f32 %1, %8, %10, %1;\n\t@p fma.rn.f32 %2, %8, %11, %2;\n\t"
+        "@p fma.rn.f32 %3, %8, %12, %3;\n\t@p fma.rn.f32 %4, %8, %13, %4;\n\t@p fma.rn.f32 %5, %8, %14, %5;\n\t"
+        "@p fma.rn.f32 %6, %8, %15, %6;\n\t@p fma.rn.f32 %7, %8, %16, %7;\n\t}"
+        : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+        : "f"(c), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7), "r"(live));
+}
+
+// one exchange of 4 published records (4 lanes x 8 bf16 channels per row), dead corners skipped
+template <int ROWB>
+__device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch,
+                                                 const char *vbase, float (&acc)[8], uint4 (&v)[4])
+{
+    const unsigned rowb = ROWB ? (unsigned)ROWB : rowbytes_rt;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
+        const char *pt = vbase + (ptrdiff_t)(int)(r.x & ~15u);
+        const char *pb = pt + pitch;
+        const float lw = __uint_as_float(r.w), hw = 1.f - lw;
+        const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
+        const float c[4] = {whh * hw, whh * lw, wlh * hw, wlh * lw};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ldg_u4_if(v[e], ((e & 2) ? pb : pt) + ((e & 1) ? rowb : 0u), r.x & (1u << e));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fma8_bf16_if(acc, c[e], v[e], r.x & (1u << e));
+    }
+}
+
+template <int QPG, class SlotSrc, int ROWB>
+__global__ void __launch_bounds__(256) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
+{
+    constexpr int LPG = 4;
+    extern __shared__ int4 s_slot[];
+    const int outer = blockIdx.y;
+    build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
+    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16::kWordsPerWarpBuf);
+
+    const int M = a.d.M, Lq = a.d.Lq;
+    const int j = threadIdx.x & 3, g = (threadIdx.x & 31) >> 2, grp = threadIdx.x >> 2, QC = blockDim.x >> 2;
+    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
+
+    int q[QPG];
+    bool qlive[QPG];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        const int qi = (qchunk * QPG + i) * QC + grp;
+        qlive[i] = qi < Lq;
+        q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
+    }
+
+    constexpr unsigned kLaneBytes = 16u;                       // 8 bf16 channels
+    const unsigned rowbytes = ROWB ? (unsigned)ROWB : (unsigned)(M * LPG) * kLaneBytes;
+    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kLaneBytes;
+    asm volatile("" : "+l"(vbase));
+
+    float acc[QPG][8];
+#pragma unroll
+    for (int i = 0; i < QPG; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+    uint4 v[4];                                                // gather destinations (see ldg_f4_if)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = make_uint4(0u, 0u, 0u, 0u);
+
+    int slot_base = 0, parity = 0;
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);   // P % 4 == 0 (checked by the launcher)
+        const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
+        const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
+        for (int k0 = 0; k0 < K; k0 += LPG) {
+            const int k = k0 + j;                                // always < K
+            const int4 sl = s_slot[slot_base + div_p(k0, P, pshift)];          // one slot for the whole exchange
+            const unsigned pitch = (unsigned)sl.y * rowbytes;
+#pragma unroll
+            for (int i = 0; i < QPG; ++i) {
+                const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+                float2 xy = make_float2(0.f, 0.f);
+                float w = 0.f;
+                if (qlive[i]) {
+                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
+                    w = ld_stream_f(aw + row * K + k);
+                }
+                const TapGeomV t = tap_geometry_v(xy.x, xy.y, sl, qlive[i]);
+                float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
+                parity ^= 1;
+                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16v(t, w, rowbytes);
+                __syncwarp();
+                consume_tap16x4v<ROWB>(buf, g, rowbytes, pitch, vbase, acc[i], v);
+            }
+        }
+        slot_base += a.seg[sg].n_slots;
+    }
+
+#pragma unroll
+    for (int i = 0; i < QPG; ++i) {
+        if (!qlive[i]) continue;
+        const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
+        const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+        reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+}
+
 }  // namespace devis

@@ -297,9 +297,11 @@ __global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 
 
 // Four lanes per (query, head), 8 channels per lane (msda_fwd8_kernel's shape): the forward of choice for bf16 value,
 // whose 64-byte rows cost 0.75 instead of 1.0 data-pipe cycles when 4 lanes fetch 16 bytes each.
-template <bool BF16>
+// ROWB >= 0 (bf16 value only): dead corners skipped, consume_tap16x4v; -1: round-1 consumer
+template <bool BF16, int ROWB = -1>
 __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a)
 {
+    static_assert(ROWB < 0 || BF16, "the dead-corner consumer of the 4-lane shape is bf16 only");
     constexpr int LPG = 4;
     extern __shared__ int4 s_slot[];
     const int outer = blockIdx.y, n_slots_total = a.n_slots[0] + (a.n_seg > 1 ? a.n_slots[1] : 0);
@@ -325,6 +327,9 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    uint4 v[4];                             // gather destinations of consume_tap16x4v
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = make_uint4(0u, 0u, 0u, 0u);
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
@@ -338,12 +343,19 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
             const RawTap cur = load_raw_tap<false>(a, sg, row, qrow, k, qlive);
             float x = 0.f, y = 0.f, w = 0.f;
             if (qlive) raw_to_operands<false>(a, sg, cur, sl, rmax, rinv, x, y, w);
-            const TapGeom t = tap_geometry(x, y, sl, qlive);
             float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
             parity ^= 1;
-            *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16(t, w, rowbytes);
-            __syncwarp();
-            consume_tap16x4<BF16>(buf, g, rowbytes, pitch, vbase, acc);
+            if (ROWB >= 0) {
+                const TapGeomV t = tap_geometry_v(x, y, sl, qlive);
+                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16v(t, w, rowbytes);
+                __syncwarp();
+                consume_tap16x4v<(ROWB > 0 ? ROWB : 0)>(buf, g, rowbytes, pitch, vbase, acc, v);
+            } else {
+                const TapGeom t = tap_geometry(x, y, sl, qlive);
+                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16(t, w, rowbytes);
+                __syncwarp();
+                consume_tap16x4<BF16>(buf, g, rowbytes, pitch, vbase, acc);
+            }
         }
         slot_base += a.n_slots[sg];
     }
