@@ -81,6 +81,9 @@ int devis_capi_check_launch(int family)
 #ifndef DEVIS_FWD_VIRTUAL
 #define DEVIS_FWD_VIRTUAL 1
 #endif
+#ifndef DEVIS_FWD_WIDE_F32
+#define DEVIS_FWD_WIDE_F32 0    // 1: fp32 value takes the four-lane x 8-channel shape too (A/B)
+#endif
 // compile-time A/B of the launch shape of msda_fwdv_kernel (benchmarks/build_variants.py); 0 = pick_shape decides
 #ifndef DEVIS_FWDV_THREADS
 #define DEVIS_FWDV_THREADS 0
@@ -152,10 +155,14 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     // row), fp32 +-1 % local / +10 % uniform taps (LDG.256 costs 1.18 wavefronts per 128-B row against 1.01 for
     // LDG.128, which eats what the smaller tap record saves) -> default: bf16 only.  Tuning key 4: 1 never, 2 always.
     const int wide_mode = g_tuning[4].load();
-    bool wide = lpg == 8 && (wide_mode == 2 || (wide_mode == 0 && dtype == DEVIS_MSDA_BF16));
+    bool wide = lpg == 8 && (wide_mode == 2 || (wide_mode == 0 && (dtype == DEVIS_MSDA_BF16 || DEVIS_FWD_WIDE_F32)));
     for (int sg = 0; sg < a.n_seg; ++sg) wide = wide && (a.seg[sg].P % 4 == 0);
     if (wide) {
-        const LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 2, 0, 1);
+        LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 2, 0, 1);
+        if (dtype != DEVIS_MSDA_BF16) {      // compile-time A/B of the fp32 launch shape (benchmarks/build_variants.py)
+            if (DEVIS_FWDV_THREADS && s.threads > DEVIS_FWDV_THREADS) s.threads = DEVIS_FWDV_THREADS;
+            if (DEVIS_FWDV_QPG && s.qpg > DEVIS_FWDV_QPG) s.qpg = DEVIS_FWDV_QPG;
+        }
         smem += (size_t)(s.threads / 32) * Tap16::kBytesPerWarp;
         const int qc = s.threads / 4;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
@@ -163,15 +170,21 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
         const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
 #define DEVIS_FWD8(BF, QPG) msda_fwd8_kernel<BF, QPG, SlotSrc><<<grid, s.threads, smem, st>>>(a)
 #if DEVIS_FWD_VIRTUAL
-        // round 2: bf16 value with the dead corners skipped (msda_fwd8v_kernel); signed offsets -> value < 2 GiB
-        if (dtype == DEVIS_MSDA_BF16 && (unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31)) {
-            if (d.M == 8) {
-                if (s.qpg == 2) msda_fwd8v_kernel<2, SlotSrc, 512><<<grid, s.threads, smem, st>>>(a);
-                else msda_fwd8v_kernel<1, SlotSrc, 512><<<grid, s.threads, smem, st>>>(a);
+        // round 2: the four-lane shape with the dead corners skipped (msda_fwd8v_kernel); signed offsets -> value < 2 GiB
+        if ((unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31)) {
+#define DEVIS_FWD8V(BF, QPG)                                                                                  \
+    do {                                                                                                      \
+        if (d.M == 8) msda_fwd8v_kernel<BF, QPG, SlotSrc, (BF ? 512 : 1024)><<<grid, s.threads, smem, st>>>(a); \
+        else msda_fwd8v_kernel<BF, QPG, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);                        \
+    } while (0)
+            if (dtype == DEVIS_MSDA_BF16) {
+                if (s.qpg == 2) DEVIS_FWD8V(true, 2);
+                else DEVIS_FWD8V(true, 1);
             } else {
-                if (s.qpg == 2) msda_fwd8v_kernel<2, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);
-                else msda_fwd8v_kernel<1, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);
+                if (s.qpg == 2) DEVIS_FWD8V(false, 2);
+                else DEVIS_FWD8V(false, 1);
             }
+#undef DEVIS_FWD8V
             return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
         }
 #endif

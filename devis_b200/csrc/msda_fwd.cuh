@@ -19,6 +19,7 @@
 // temporal op (SlotSrc = ClipTable, two segments, value indexed through the frame table).
 #pragma once
 #include "msda_common.cuh"
+#include <type_traits>
 
 #ifndef DEVIS_FWD_TAP_BATCH
 #define DEVIS_FWD_TAP_BATCH 2
@@ -756,6 +757,45 @@ __device__ __forceinline__ void fma8_bf16_if(float (&acc)[8], float c, const uin
         : "f"(c), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7), "r"(live));
 }
 
+// fp32 value, 8 channels per lane: one predicated 32-byte gather (LDG.E.256)
+struct F8 {
+    float f[8];
+};
+__device__ __forceinline__ void ldg_f8_if(F8 &v, const char *p, unsigned live)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t@p ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+        : "+f"(v.f[0]), "+f"(v.f[1]), "+f"(v.f[2]), "+f"(v.f[3]), "+f"(v.f[4]), "+f"(v.f[5]), "+f"(v.f[6]), "+f"(v.f[7])
+        : "l"(p), "r"(live));
+}
+__device__ __forceinline__ void fma8_if(float (&acc)[8], float c, const F8 &v, unsigned live)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %17, 0;\n\t"
+        "@p fma.rn.f32 %0, %8, %9, %0;\n\t@p fma.rn.f32 %1, %8, %10, %1;\n\t@p fma.rn.f32 %2, %8, %11, %2;\n\t"
+        "@p fma.rn.f32 %3, %8, %12, %3;\n\t@p fma.rn.f32 %4, %8, %13, %4;\n\t@p fma.rn.f32 %5, %8, %14, %5;\n\t"
+        "@p fma.rn.f32 %6, %8, %15, %6;\n\t@p fma.rn.f32 %7, %8, %16, %7;\n\t}"
+        : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+        : "f"(c), "f"(v.f[0]), "f"(v.f[1]), "f"(v.f[2]), "f"(v.f[3]), "f"(v.f[4]), "f"(v.f[5]), "f"(v.f[6]), "f"(v.f[7]), "r"(live));
+}
+template <int ROWB>
+__device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch,
+                                                 const char *vbase, float (&acc)[8], F8 (&v)[4])
+{
+    const unsigned rowb = ROWB ? (unsigned)ROWB : rowbytes_rt;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
+        const char *pt = vbase + (ptrdiff_t)(int)(r.x & ~15u);
+        const char *pb = pt + pitch;
+        const float lw = __uint_as_float(r.w), hw = 1.f - lw;
+        const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
+        const float c[4] = {whh * hw, whh * lw, wlh * hw, wlh * lw};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ldg_f8_if(v[e], ((e & 2) ? pb : pt) + ((e & 1) ? rowb : 0u), r.x & (1u << e));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fma8_if(acc, c[e], v[e], r.x & (1u << e));
+    }
+}
+
 // one exchange of 4 published records (4 lanes x 8 bf16 channels per row), dead corners skipped
 template <int ROWB>
 __device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch,
@@ -777,8 +817,11 @@ __device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsign
     }
 }
 
-template <int QPG, class SlotSrc, int ROWB>
-__global__ void __launch_bounds__(256) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
+#ifndef DEVIS_FWD8V_F32_MIN_BLOCKS
+#define DEVIS_FWD8V_F32_MIN_BLOCKS 2
+#endif
+template <bool BF16, int QPG, class SlotSrc, int ROWB>
+__global__ void __launch_bounds__(256, BF16 ? 1 : DEVIS_FWD8V_F32_MIN_BLOCKS) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
 {
     constexpr int LPG = 4;
     extern __shared__ int4 s_slot[];
@@ -799,7 +842,7 @@ __global__ void __launch_bounds__(256) msda_fwd8v_kernel(const FwdArgs<SlotSrc> 
         q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
     }
 
-    constexpr unsigned kLaneBytes = 16u;                       // 8 bf16 channels
+    constexpr unsigned kLaneBytes = BF16 ? 16u : 32u;          // 8 channels
     const unsigned rowbytes = ROWB ? (unsigned)ROWB : (unsigned)(M * LPG) * kLaneBytes;
     const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kLaneBytes;
     asm volatile("" : "+l"(vbase));
@@ -809,9 +852,10 @@ __global__ void __launch_bounds__(256) msda_fwd8v_kernel(const FwdArgs<SlotSrc> 
     for (int i = 0; i < QPG; ++i)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
-    uint4 v[4];                                                // gather destinations (see ldg_f4_if)
+    // gather destinations (see ldg_f4_if): raw bf16x8 or eight floats per corner
+    typename std::conditional<BF16, uint4, F8>::type v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = 0; e < 4; ++e) v[e] = {};
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
@@ -846,9 +890,15 @@ __global__ void __launch_bounds__(256) msda_fwd8v_kernel(const FwdArgs<SlotSrc> 
     for (int i = 0; i < QPG; ++i) {
         if (!qlive[i]) continue;
         const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
-        const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-        const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
-        reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        if (BF16) {
+            const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+            reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+            float4 *o = reinterpret_cast<float4 *>(a.out) + (row * LPG + j) * 2;
+            st_stream_f4(o, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            st_stream_f4(o + 1, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+        }
     }
 }
 
