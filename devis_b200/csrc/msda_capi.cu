@@ -804,6 +804,13 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
     return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
 }
 
+size_t devis_tmsda_fused_backward_workspace_bytes(int num_frames, int spatial_size, int num_heads, int channels, unsigned flags)
+{
+    if (!(flags & DEVIS_MSDA_FLAG_DETERMINISTIC) || (flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE)) return 0;
+    if (num_frames < 0 || spatial_size < 0 || num_heads < 0 || channels < 0) return 0;
+    return det_workspace_bytes(num_frames, spatial_size, num_heads, channels);
+}
+
 int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_host,
                                const int64_t *level_start_index_host, const int32_t *frame_table_host,
                                const void *ref, const void *off_curr, const void *logit_curr,
@@ -813,7 +820,7 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
                                const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
                                int channels, int num_levels, int num_query, int n_curr_points,
                                int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
-                               unsigned flags, void *stream)
+                               unsigned flags, void *workspace, size_t workspace_bytes, void *stream)
 {
     FusedArgs a{};
     int rc = fill_fused(a, value, spatial_shapes_host, level_start_index_host, frame_table_host, ref, off_curr,
@@ -821,11 +828,35 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
                         channels, num_levels, num_query, n_curr_points, n_temporal_points, t_window, ref_dim,
                         temporal_ref_mode, dtype);
     if (rc) return rc;
-    if (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) return DEVIS_MSDA_ERR_UNSUPPORTED;
     const bool want_gv = !(flags & DEVIS_MSDA_FLAG_NO_GRAD_VALUE);
     const bool half_acc = want_gv && (flags & DEVIS_MSDA_FLAG_BF16_GRAD_VALUE);
     if (half_acc && dtype != DEVIS_MSDA_BF16) return DEVIS_MSDA_ERR_UNSUPPORTED;
+    // deterministic mode: grad_value through 64-bit fixed point (workspace); d/d(ref) is a float-atomic sum over
+    // queries' heads and taps and has no fixed-point form here
+    const bool det = (flags & DEVIS_MSDA_FLAG_DETERMINISTIC) && want_gv;
+    if ((flags & DEVIS_MSDA_FLAG_DETERMINISTIC) && (grad_ref || half_acc)) return DEVIS_MSDA_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_value = (size_t)num_frames * spatial_size * num_heads * channels;
+    if (det) {
+        const size_t need = det_workspace_bytes(num_frames, spatial_size, num_heads, channels);
+        if (!workspace || workspace_bytes < need) return DEVIS_MSDA_ERR_WORKSPACE;
+        const cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+        if (e != cudaSuccess) return cuda_fail(e);
+        a.det.acc = reinterpret_cast<long long *>(workspace);
+        unsigned *slots = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(workspace) + n_value * sizeof(long long));
+        a.det.max_bits = slots;
+        if (num_frames > 0 && num_query > 0) {
+            const size_t n_go = (size_t)num_frames * num_query * num_heads * channels;
+            const int blocks = devis_capi_helper_blocks();
+            if (dtype == DEVIS_MSDA_BF16) absmax_kernel<true><<<blocks, 256, 0, st>>>(grad_output, n_go, slots);
+            else absmax_kernel<false><<<blocks, 256, 0, st>>>(grad_output, n_go, slots);
+            rc = check_launch(DEVIS_MSDA_KERNEL_AUX);
+            if (rc) return rc;
+            set_word_kernel<<<1, 1, 0, st>>>(slots + 1, 0x3f800000u);      // max|attn| = 1: softmax outputs
+            rc = check_launch(DEVIS_MSDA_KERNEL_AUX);
+            if (rc) return rc;
+        }
+    }
     if (want_gv) {
         const size_t bytes = (size_t)num_frames * spatial_size * num_heads * channels * (half_acc ? 2 : sizeof(float));
         if (bytes && !grad_value) return DEVIS_MSDA_ERR_NULL_POINTER;
@@ -866,6 +897,20 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
         }
     }
     const bool general = ref_dim == 4 || (a.n_seg > 1 && temporal_ref_mode != 0) || grad_ref;
+    if (det) {
+        if (general) {
+            if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true, false, true, true><<<grid, threads, smem, st>>>(a);
+            else tmsda_fused_bwd_kernel<false, false, true, true><<<grid, threads, smem, st>>>(a);
+        } else {
+            if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true, false, false, true><<<grid, threads, smem, st>>>(a);
+            else tmsda_fused_bwd_kernel<false, false, false, true><<<grid, threads, smem, st>>>(a);
+        }
+        rc = check_launch(DEVIS_MSDA_KERNEL_FUSED_BWD);
+        if (rc || n_value == 0) return rc;
+        det_finalize_kernel<<<devis_capi_helper_blocks(), 256, 0, st>>>(a.det.acc, reinterpret_cast<float *>(grad_value), n_value,
+                                                                       a.det.max_bits, 8);
+        return check_launch(DEVIS_MSDA_KERNEL_AUX);
+    }
     if (general) {
         if (half_acc) tmsda_fused_bwd_kernel<true, true, true><<<grid, threads, smem, st>>>(a);
         else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_bwd_kernel<true, false, true><<<grid, threads, smem, st>>>(a);

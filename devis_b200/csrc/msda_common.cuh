@@ -514,6 +514,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const void *x, size_t n, un
     if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
 }
 
+__global__ void set_word_kernel(unsigned *slot, unsigned bits) { *slot = bits; }
+
 // lpg > 0: the accumulators of every D = 4*lpg channels are in the permuted order of det_add4; lpg == 0: channel order
 __global__ void __launch_bounds__(256) det_finalize_kernel(const long long *acc, float *out, size_t n,
                                                            const unsigned *max_bits, int lpg)

@@ -51,6 +51,7 @@ struct FusedArgs {
     // backward
     const void *grad_out;
     void *grad_value;          // fp32 (bf16 under HALF_ACC)
+    DetScale det;              // deterministic mode (DET kernels): 64-bit fixed-point accumulators replace grad_value
     float *grad_off[2];
     float *grad_logit[2];
     int park_iters;            // > 0: shared memory holds (weight, d/d weight) of that many exchanges per thread
@@ -373,9 +374,14 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
 }
 
 // HALF_ACC: bf16 grad_value with packed bf16 reductions (see msda_bwd_kernel)
-template <bool BF16, bool HALF_ACC = false, bool GEN = false>
+// DET (round 2): DEVIS_MSDA_FLAG_DETERMINISTIC inside the fused path -- the grad_value contributions go to 64-bit
+// fixed-point accumulators with integer reductions (det_add4, msda_common.cuh) exactly as in msda_bwd_kernel, with the
+// bound max|attn| = 1 (the weights are softmax outputs here); every other gradient of this kernel is written once, in a
+// fixed order, so the whole backward is bit-identical run to run.
+template <bool BF16, bool HALF_ACC = false, bool GEN = false, bool DET = false>
 __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_kernel(const FusedArgs a)
 {
+    static_assert(!(DET && HALF_ACC), "deterministic mode accumulates in fixed point");
     constexpr int LPG = 8;
     using X = TapExchange<LPG>;
     extern __shared__ int4 s_slot[];
@@ -410,6 +416,9 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
     static_assert(!HALF_ACC || BF16, "bf16 accumulation needs bf16 value");
     char *gvb = a.grad_value ? reinterpret_cast<char *>(a.grad_value) + (size_t)(m * LPG + j) * (HALF_ACC ? 8u : 16u) : nullptr;
     constexpr unsigned kGvShift = (BF16 && !HALF_ACC) ? 1u : 0u;
+    // deterministic mode: 8-byte accumulators, channels of a (row, head) permuted as in det_add4 (lane j starts at word j)
+    char *detb = DET ? reinterpret_cast<char *>(a.det.acc) + (size_t)(m * LPG) * 32u + (size_t)j * 8u : nullptr;
+    const float det_sh = DET ? ldexpf(1.f, kDetFracBits - det_exponent(a.det.max_bits)) : 0.f;
 
     float rmax, rinv;
     row_softmax_stats(a, row, j, qlive, rmax, rinv);
@@ -459,7 +468,12 @@ __global__ void __launch_bounds__(256, DEVIS_BWD_MIN_BLOCKS) tmsda_fused_bwd_ker
                 dsum[jj][1] = fmaf(v01.w, gg.w, fmaf(v01.z, gg.z, fmaf(v01.y, gg.y, v01.x * gg.x)));
                 dsum[jj][2] = fmaf(v10.w, gg.w, fmaf(v10.z, gg.z, fmaf(v10.y, gg.y, v10.x * gg.x)));
                 dsum[jj][3] = fmaf(v11.w, gg.w, fmaf(v11.z, gg.z, fmaf(v11.y, gg.y, v11.x * gg.x)));
-                if (gvb) {
+                if (DET) {
+                    if (c.x != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.x << (kGvShift + 1))), det_sh, c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
+                    if (c.y != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.y << (kGvShift + 1))), det_sh, c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
+                    if (c.z != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.z << (kGvShift + 1))), det_sh, c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);
+                    if (c.w != 0.f) det_add4<LPG>(reinterpret_cast<long long *>(detb + ((size_t)off.w << (kGvShift + 1))), det_sh, c.w * gg.x, c.w * gg.y, c.w * gg.z, c.w * gg.w);
+                } else if (gvb) {
                     if (c.x != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.x << kGvShift), c.x * gg.x, c.x * gg.y, c.x * gg.z, c.x * gg.w);
                     if (c.y != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.y << kGvShift), c.y * gg.x, c.y * gg.y, c.y * gg.z, c.y * gg.w);
                     if (c.z != 0.f) red_add_quad<HALF_ACC>(gvb + ((size_t)off.z << kGvShift), c.z * gg.x, c.z * gg.y, c.z * gg.z, c.z * gg.w);

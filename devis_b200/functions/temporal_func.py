@@ -139,7 +139,9 @@ class TemporalMSDeformAttnFusedFunction(Function):
         return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16) and value.shape[-1] == 32
                 and n_curr_points % 4 == 0 and n_temporal_points % 4 == 0
                 and reference_points.shape[-1] in (2, 4) and value.numel() * value.element_size() < (1 << 32)
-                and not MSDA.deterministic_enabled(value.dtype))
+                # deterministic mode: grad_value goes through fixed point inside the kernel; d/d(reference points) is a
+                # float-atomic sum there, so learnable reference points take the unfused path in that mode
+                and not (MSDA.deterministic_enabled(value.dtype) and reference_points.requires_grad))
 
     @staticmethod
     def forward(ctx, value, ref, off_curr, logit_curr, off_temporal, logit_temporal, geometry, query_order=None,
@@ -202,19 +204,26 @@ class TemporalMSDeformAttnFusedFunction(Function):
         need_gv = ctx.needs_input_grad[0]
         need_gref = ctx.needs_input_grad[1]
         half_acc = need_gv and MSDA.bf16_accumulate_enabled(value)
+        det = MSDA.deterministic_enabled(value.dtype)
+        if det and need_gref:
+            raise RuntimeError("temporal_ms_deform_attn_fused: deterministic mode has no gradient for the reference points "
+                               "(use the unfused path: TemporalMSDeformAttnFusedFunction.supported() says so)")
         gv = torch.empty(value.shape, dtype=value.dtype if half_acc else torch.float32, device=value.device) \
             if need_gv else None
         goc, glc = torch.empty_like(oc), torch.empty_like(lc)
         got = torch.empty_like(ot) if has_t else None
         glt = torch.empty_like(lt) if has_t else None
         gref = torch.empty_like(ref) if need_gref else None
+        flags = (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE) | (_lib.FLAG_BF16_GRAD_VALUE if half_acc else 0) | \
+            (_lib.FLAG_DETERMINISTIC if det else 0)
         with torch.cuda.device(value.device):
+            ws_bytes = _lib.load().devis_tmsda_fused_backward_workspace_bytes(t, s, m, d, flags)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
             _lib.check(_lib.load().devis_tmsda_fused_backward(
                 _ptr(value), geometry.shapes_ptr, geometry.lsi_ptr, geometry.frames_ptr, _ptr(ref), _ptr(oc), _ptr(lc),
                 _ptr(ot), _ptr(lt), _ptr(gout), _ptr(gv), _ptr(goc), _ptr(glc), _ptr(got), _ptr(glt), _ptr(gref),
                 _ptr(query_order), t, s, m, d, geometry.n_levels, lq, pc, pt, geometry.t_window if has_t else 0,
-                ref_dim, ctx.tref, _DTYPES[value.dtype],
-                (0 if need_gv else _lib.FLAG_NO_GRAD_VALUE) | (_lib.FLAG_BF16_GRAD_VALUE if half_acc else 0),
+                ref_dim, ctx.tref, _DTYPES[value.dtype], flags, _ptr(ws), ws_bytes,
                 torch.cuda.current_stream().cuda_stream))
         doc, dlc, dot, dlt, dref = ctx.in_dtypes
         if gv is not None and gv.dtype != value.dtype:

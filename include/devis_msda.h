@@ -189,7 +189,9 @@ int devis_tmsda_backward(const void *value, const int64_t *spatial_shapes_host,
  * value / output / grad_output: DEVIS_MSDA_F32 or DEVIS_MSDA_BF16; channels must be 32 and the point counts multiples of
  * 4 (else DEVIS_MSDA_ERR_UNSUPPORTED and the caller uses devis_tmsda_forward on materialised operands).  The backward
  * writes d/d(off_*) and d/d(logit_*) directly; grad_value (float) is zero-filled by the call; flags:
- * DEVIS_MSDA_FLAG_NO_GRAD_VALUE, DEVIS_MSDA_FLAG_BF16_GRAD_VALUE (DETERMINISTIC -> DEVIS_MSDA_ERR_UNSUPPORTED).
+ * DEVIS_MSDA_FLAG_NO_GRAD_VALUE, DEVIS_MSDA_FLAG_BF16_GRAD_VALUE, DEVIS_MSDA_FLAG_DETERMINISTIC (round 2: grad_value
+ * through exact 64-bit fixed point in `workspace` of devis_tmsda_fused_backward_workspace_bytes, bit-identical run to run;
+ * with grad_ref or BF16_GRAD_VALUE -> DEVIS_MSDA_ERR_UNSUPPORTED).  workspace may be NULL when the byte count is 0.
  */
 #define DEVIS_TMSDA_TREF_LEVEL0 0
 #define DEVIS_TMSDA_TREF_OWN 1
@@ -203,6 +205,8 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
                               int channels, int num_levels, int num_query, int n_curr_points,
                               int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
                               void *stream);
+size_t devis_tmsda_fused_backward_workspace_bytes(int num_frames, int spatial_size, int num_heads, int channels,
+                                                  unsigned flags);
 int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_host,
                                const int64_t *level_start_index_host, const int32_t *frame_table_host,
                                const void *ref, const void *off_curr, const void *logit_curr,
@@ -212,7 +216,7 @@ int devis_tmsda_fused_backward(const void *value, const int64_t *spatial_shapes_
                                const int32_t *query_order, int num_frames, int spatial_size, int num_heads,
                                int channels, int num_levels, int num_query, int n_curr_points,
                                int n_temporal_points, int t_window, int ref_dim, int temporal_ref_mode, int dtype,
-                               unsigned flags, void *stream);
+                               unsigned flags, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }
