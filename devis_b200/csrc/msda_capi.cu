@@ -228,11 +228,8 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
                 if (s.qpg == 2) DEVIS_FWDV(true, 2);
                 else DEVIS_FWDV(true, 1);
             } else {
-#if !DEVIS_FWDV_PREFETCH
                 if (s.qpg == 4) DEVIS_FWDV(false, 4);
-                else
-#endif
-                if (s.qpg >= 2) DEVIS_FWDV(false, 2);
+                else if (s.qpg == 2) DEVIS_FWDV(false, 2);
                 else DEVIS_FWDV(false, 1);
             }
 #undef DEVIS_FWDV

@@ -340,9 +340,6 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
 #ifndef DEVIS_FWDV_MAXT
 #define DEVIS_FWDV_MAXT 256
 #endif
-#ifndef DEVIS_FWDV_PREFETCH
-#define DEVIS_FWDV_PREFETCH 0
-#endif
 #ifndef DEVIS_FWDV_TB
 #define DEVIS_FWDV_TB 1
 #endif
@@ -373,26 +370,12 @@ __device__ __forceinline__ void ldg_bf16x4_if(float4 &v, const char *p, unsigned
     v.z = __uint_as_float(hi << 16);
     v.w = __uint_as_float(hi & 0xffff0000u);
 }
-#ifndef DEVIS_FWDV_FFMA2
-#define DEVIS_FWDV_FFMA2 0
-#endif
 __device__ __forceinline__ void fma4_if(float4 &acc, float c, const float4 &v, unsigned live)
 {
-#if DEVIS_FWDV_FFMA2
-    // packed fp32 pairs (fma.rn.f32x2, new on sm_100): two instructions per corner instead of four
-    asm("{\n\t.reg .pred p;\n\t.reg .b64 cc, v01, v23, a01, a23;\n\tsetp.ne.u32 p, %9, 0;\n\t"
-        "mov.b64 cc, {%4, %4};\n\tmov.b64 v01, {%5, %6};\n\tmov.b64 v23, {%7, %8};\n\t"
-        "mov.b64 a01, {%0, %1};\n\tmov.b64 a23, {%2, %3};\n\t"
-        "@p fma.rn.f32x2 a01, cc, v01, a01;\n\t@p fma.rn.f32x2 a23, cc, v23, a23;\n\t"
-        "mov.b64 {%0, %1}, a01;\n\tmov.b64 {%2, %3}, a23;\n\t}"
-        : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
-        : "f"(c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(live));
-#else
     asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
         "@p fma.rn.f32 %0, %4, %5, %0;\n\t@p fma.rn.f32 %1, %4, %6, %1;\n\t@p fma.rn.f32 %2, %4, %7, %2;\n\t@p fma.rn.f32 %3, %4, %8, %3;\n\t}"
         : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
         : "f"(c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(live));
-#endif
 }
 
 // TB = taps whose gathers are in flight together (v: their destinations, owned by the kernel)
@@ -519,29 +502,6 @@ __global__ void __launch_bounds__(DEVIS_FWDV_MAXT, DEVIS_FWDV_MIN_BLOCKS) msda_f
             for (int i = 0; i < QPG; ++i) cur[i] = nxt[i];
             if (k0 + LPG < K) load_taps(sg, k0 + LPG, nxt);
             else if (sg + 1 < a.n_seg) load_taps(sg + 1, 0, nxt);
-#if DEVIS_FWDV_PREFETCH
-            // EXPERIMENT: all QPG records are published first and the producing lane asks for its tap's live rows
-            // (prefetch.global.L1, no destination register, no scoreboard), so that the gathers of the later taps find
-            // their lines in L1 instead of waiting ~400 cycles for L2
-            static_assert(QPG <= 2, "two exchange buffers");
-#pragma unroll
-            for (int i = 0; i < QPG; ++i) {
-                const TapGeomV t = tap_geometry_v(cur[i].xy.x, cur[i].xy.y, sl, klive && qlive[i]);
-                const uint4 rec = make_tap16v(t, cur[i].w, rowbytes);
-                *reinterpret_cast<uint4 *>(xbuf + i * Tap16x8::kWordsPerWarpBuf + Tap16x8::word(j, g)) = rec;
-                const char *pt = vbase + (ptrdiff_t)(int)(rec.x & ~15u);
-                const char *pb = pt + my_pitch;
-                if (rec.x & 1u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pt));
-                if (rec.x & 2u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pt + rowbytes));
-                if (rec.x & 4u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb));
-                if (rec.x & 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + rowbytes));
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < QPG; ++i)
-                consume_tap16v<BF16, ROWB, DEVIS_FWDV_TB>(xbuf + i * Tap16x8::kWordsPerWarpBuf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
-            __syncwarp();
-#else
 #pragma unroll
             for (int i = 0; i < QPG; ++i) {
                 const TapGeomV t = tap_geometry_v(cur[i].xy.x, cur[i].xy.y, sl, klive && qlive[i]);
@@ -551,7 +511,6 @@ __global__ void __launch_bounds__(DEVIS_FWDV_MAXT, DEVIS_FWDV_MIN_BLOCKS) msda_f
                 __syncwarp();
                 consume_tap16v<BF16, ROWB, DEVIS_FWDV_TB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
             }
-#endif
         }
         slot_base += a.seg[sg].n_slots;
     }
