@@ -155,3 +155,29 @@ def test_out_of_range_taps_do_not_read_the_map():
     out = MSDeformAttnFunction.apply(poisoned, shp, lsi, loc, aw, 64)
     assert torch.isfinite(out).all()
     assert torch.equal(out, clean)
+
+
+@pytest.mark.parametrize("rows_h", [1900, 2100])
+def test_forward_addresses_near_the_two_gib_boundary(rows_h):
+    """The round-2 forward keeps SIGNED 32-bit byte offsets (a virtual top-left cell may lie before the map), so it serves
+    value tensors below 2 GiB and hands larger ones to the unsigned-offset kernel (below 4 GiB).  1.95 GB and 2.15 GB of
+    value, taps in the last rows of the map: the result must equal the same taps evaluated on a copy of just those rows."""
+    from devis_b200 import MSDeformAttnFunction
+    m, d, p, w, tail, lq = 8, 32, 4, 1000, 8, 64
+    g = torch.Generator(device="cuda").manual_seed(rows_h)
+    value = torch.empty(1, rows_h * w, m, d, device="cuda")
+    value[:, -tail * w:] = torch.randn(1, tail * w, m, d, device="cuda", generator=g)
+    shp_big = torch.tensor([[rows_h, w]], device="cuda")
+    shp_small = torch.tensor([[tail, w]], device="cuda")
+    lsi = torch.zeros(1, dtype=torch.long, device="cuda")
+    # pixel coordinates inside the last `tail` rows, at least one row away from the slice's upper edge
+    py = rows_h - tail + 1.25 + torch.rand(1, lq, m, 1, p, device="cuda", generator=g) * (tail - 2.5)
+    px = torch.rand(1, lq, m, 1, p, device="cuda", generator=g) * (w - 1.0) + 0.25
+    loc_big = torch.stack([(px + 0.5) / w, (py + 0.5) / rows_h], -1).contiguous()
+    loc_small = torch.stack([(px + 0.5) / w, (py - (rows_h - tail) + 0.5) / tail], -1).contiguous()
+    aw = torch.softmax(torch.randn(1, lq, m, p, device="cuda", generator=g), -1).view(1, lq, m, 1, p).contiguous()
+    out_big = MSDeformAttnFunction.apply(value, shp_big, lsi, loc_big, aw, 64)
+    out_small = MSDeformAttnFunction.apply(value[:, -tail * w:].contiguous(), shp_small, lsi, loc_small, aw, 64)
+    # the two calls round y differently (y * H in float32 at H = 1900 vs 8): compare at that resolution
+    assert nmax(out_big.cpu().numpy(), out_small.cpu().numpy()) < 2e-3
+    assert torch.isfinite(out_big).all()
