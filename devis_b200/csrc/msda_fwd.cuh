@@ -776,11 +776,13 @@ __device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsign
     }
 }
 
+// (bf16: NO minimum-blocks hint (0): ptxas settles at 62 registers, 359 us; a hint of 1 makes it unroll to 184 registers and 711 us,
+// a hint of 4 (64-register cap) gives 371 us)
 #ifndef DEVIS_FWD8V_F32_MIN_BLOCKS
 #define DEVIS_FWD8V_F32_MIN_BLOCKS 2
 #endif
 template <bool BF16, int QPG, class SlotSrc, int ROWB>
-__global__ void __launch_bounds__(256, BF16 ? 1 : DEVIS_FWD8V_F32_MIN_BLOCKS) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
+__global__ void __launch_bounds__(256, BF16 ? 0 : DEVIS_FWD8V_F32_MIN_BLOCKS) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
 {
     constexpr int LPG = 4;
     extern __shared__ int4 s_slot[];
