@@ -156,7 +156,11 @@ __global__ void __launch_bounds__(256) dcn_igemm_pack_kernel(const float *__rest
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIgThreads, 1) dcn_igemm_fwd_kernel(const IgArgs a)
+// MINB: thread blocks per SM the register budget is sized for.  The wide layers are bound by shared memory to one block
+// per SM; the narrow ones (few 32-channel stages per kernel position) are latency chains inside a block and want a
+// second / third block on the SM to overlap them.
+template <int MINB>
+__global__ void __launch_bounds__(kIgThreads, MINB) dcn_igemm_fwd_kernel(const IgArgs a)
 {
     extern __shared__ unsigned char ig_smem_raw[];
     // 1024-byte alignment: the swizzle pattern is a function of the address bits

@@ -424,10 +424,21 @@ namespace {
 struct IgPlan {
     bool ok = false;
     int Npad = 0, nchunks = 0, n0 = 0, n1 = 0, tmem_cols = 0;
+    // blocks per SM the launch aims for: the shared-memory budget of a block is 227 KB / blocks
+    int blocks(int split) const
+    {
+#ifdef DEVIS_IG_BLOCKS
+        (void)split;
+        return DEVIS_IG_BLOCKS;
+#else
+        const int stage = (split ? 2 : 1) * (devis::kIgATile + Npad * 128);
+        return (2 * stage + devis::kIgGeomBytes + 2048) * 2 <= 227 * 1024 ? 2 : 1;
+#endif
+    }
     int stages(int split) const
     {
         const int stage = (split ? 2 : 1) * (devis::kIgATile + Npad * 128);
-        int s = (227 * 1024 - devis::kIgGeomBytes - 256 - 1024) / stage;
+        int s = (227 * 1024 / blocks(split) - devis::kIgGeomBytes - 256 - 1024 - 1024) / stage;
         return s > devis::kIgMaxStages ? devis::kIgMaxStages : s;
     }
     size_t smem(int split) const
@@ -522,10 +533,17 @@ int devis_dcn_igemm_forward(const void *input, const void *offset, const void *m
     a.tmem_cols = p.tmem_cols;
     a.P = P;
     const size_t smem = p.smem(split);
-    const cudaError_t e = cudaFuncSetAttribute(devis::dcn_igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return devis_capi_cuda_fail(e);
     const unsigned grid = (unsigned)((P + devis::kIgBM - 1) / devis::kIgBM);
-    devis::dcn_igemm_fwd_kernel<<<grid, devis::kIgThreads, smem, (cudaStream_t)stream>>>(a);
+    const int blocks = p.blocks(split);
+    auto launch = [&](auto kernel) -> int {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return devis_capi_cuda_fail(e);
+        kernel<<<grid, devis::kIgThreads, smem, (cudaStream_t)stream>>>(a);
+        return DEVIS_MSDA_OK;
+    };
+    const int lrc = blocks >= 3 ? launch(devis::dcn_igemm_fwd_kernel<3>)
+                                : blocks == 2 ? launch(devis::dcn_igemm_fwd_kernel<2>) : launch(devis::dcn_igemm_fwd_kernel<1>);
+    if (lrc) return lrc;
     return devis_capi_check_launch(DEVIS_MSDA_KERNEL_DCN_IGEMM);
 }
 

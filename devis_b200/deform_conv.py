@@ -404,8 +404,13 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     form = _fused_form(c, cout, kh, kw, input.dtype) if n > 0 else 0
     needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (input, offset, weight, bias, mask))
     fn = FusedDeformConv2dFunction if form & 1 and (form & 2 or not needs_grad) else DeformConv2dFunction
-    # wide layers (not served by the fused CUDA-core forms): forward on the tensor cores
-    if fn is DeformConv2dFunction and not form & 1 and n > 0 and _igemm_supported(c, cout, kh, kw, input.dtype):
+    # Forward on the tensor cores (tcgen05 implicit GEMM) for the layers with enough contraction to pay for it: everything
+    # the CUDA-core fused forms do not serve, and of those they do serve the ones with K*C >= 576 and >= 32 output channels
+    # (measured, benchmarks/igemm_narrow.py: 72 -> 32 @45x80 385 us against 613 us; 32 -> 16 @90x160 629 against 486 us and
+    # 16 -> 4 623 against 246 us stay where they are).  With gradients the 72 -> 32 layer keeps the im2col form: its backward
+    # reuses the forward's columns, which is 270 us faster there than recomputing them (at 560 MB of columns for 60 instances).
+    if n > 0 and _igemm_supported(c, cout, kh, kw, input.dtype) and \
+            (not form & 1 or (c * kh * kw >= 576 and cout >= 32 and not form & 2 and not needs_grad)):
         fn = IGemmDeformConv2dFunction
     out = fn.apply(input, same(offset), same(weight), same(bias), same(mask), stride, padding, dilation)
     return out if out.dtype == out_dtype else out.to(out_dtype)

@@ -49,10 +49,11 @@ def test_igemm_matches_torchvision_fixture(name):
             assert nmax(grads[k].cpu().numpy(), g[key]) < 1e-4, k
 
 
-@pytest.mark.parametrize("c,cout,hw,n", [(264, 264, (12, 20), 6), (264, 128, (12, 20), 6), (136, 64, (23, 40), 3)])
+@pytest.mark.parametrize("c,cout,hw,n", [(264, 264, (12, 20), 6), (264, 128, (12, 20), 6), (136, 64, (23, 40), 3),
+                                         (72, 32, (45, 80), 2)])
 def test_igemm_at_mask_head_layer_shapes(c, cout, hw, n):
-    """the three wide layers of MaskHeadConv (deformable_segmentation.py:323-380): dispatch picks the tensor-core
-    forward, and it agrees with the im2col + cuBLAS fp32 form (3xTF32) / within TF32 rounding (allow_tf32)"""
+    """the three wide layers of MaskHeadConv (deformable_segmentation.py:323-380) and the 72 -> 32 layer: dispatch picks
+    the tensor-core forward, and it agrees with the CUDA-core forms (3xTF32) / within TF32 rounding (allow_tf32)"""
     from devis_b200 import _lib, deform_conv
     from devis_b200.deform_conv import deform_conv2d
     gen = torch.Generator(device="cuda").manual_seed(c + cout)
@@ -91,7 +92,10 @@ def test_igemm_at_mask_head_layer_shapes(c, cout, hw, n):
     torch.backends.cuda.matmul.allow_tf32 = False
     leaves = [t.clone().requires_grad_(True) for t in (x, off, wt, b, msk)]
     gout = torch.randn_like(want)
+    launches = _lib.kernel_launches(_lib.KERNEL_DCN_IGEMM)
     deform_conv2d(leaves[0], leaves[1], leaves[2], leaves[3], padding=1, mask=leaves[4]).backward(gout)
+    # with gradients the wide layers stay on the tensor cores (columns recomputed); 72 -> 32 keeps its columns (im2col form)
+    assert _lib.kernel_launches(_lib.KERNEL_DCN_IGEMM) == launches + (1 if c >= 128 else 0)
     old = deform_conv.set_tensor_core(False)
     try:
         ref = [t.clone().requires_grad_(True) for t in (x, off, wt, b, msk)]

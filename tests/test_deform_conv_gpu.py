@@ -80,12 +80,16 @@ def test_fused_and_im2col_forms_agree(name):
     """the two kernel families of this library on the same layer (float32), and both against the fixture"""
     from devis_b200 import deform_conv
     g = load_golden(name)
-    out_f, grads_f = _run(g, torch.float32)
-    old = deform_conv.set_fused(False)
+    tc = deform_conv.set_tensor_core(False)        # the two CUDA-core families; the tensor-core form has its own tests
     try:
-        out_u, grads_u = _run(g, torch.float32)
+        out_f, grads_f = _run(g, torch.float32)
+        old = deform_conv.set_fused(False)
+        try:
+            out_u, grads_u = _run(g, torch.float32)
+        finally:
+            deform_conv.set_fused(old)
     finally:
-        deform_conv.set_fused(old)
+        deform_conv.set_tensor_core(tc)
     assert nmax(out_f.cpu().numpy(), out_u.cpu().numpy()) < 1e-5
     for k in grads_f:
         assert nmax(grads_f[k].cpu().numpy(), grads_u[k].cpu().numpy()) < 1e-4, k
@@ -108,12 +112,14 @@ def test_fused_forward_inference_mode(name):
     calls = []
     real_pack = deform_conv._packed_weight
     deform_conv._packed_weight = lambda weight: (calls.append(1), real_pack(weight))[1]
+    tc = deform_conv.set_tensor_core(False)        # (72 -> 32 would otherwise take the tensor-core forward)
     try:
         with torch.no_grad():
             out = deform_conv2d(t("x"), t("offset"), w, t("bias"), stride=st, padding=pd, dilation=dl,
                                 mask=t("mask") if use_mask else None)
     finally:
         deform_conv._packed_weight = real_pack
+        deform_conv.set_tensor_core(tc)
     assert calls                                                                # went through the fused function
     with torch.no_grad():
         again = deform_conv2d(t("x"), t("offset"), w, None, stride=st, padding=pd, dilation=dl,
