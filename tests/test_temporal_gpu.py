@@ -340,12 +340,14 @@ def test_fused_prologue_matches_unfused_path_and_reference_module():
         assert nmax(f[3][name].cpu().numpy(), u[3][name].cpu().numpy()) < 2e-4, name
 
 
-def test_fused_function_matches_pytorch_oracle_on_small_clip():
-    """fused op vs the fp64 PyTorch oracle (projection-free): logits/offsets -> softmax/locations -> per-frame loop"""
+@pytest.mark.parametrize("M", [8, 3])
+def test_fused_function_matches_pytorch_oracle_on_small_clip(M):
+    """fused op vs the fp64 PyTorch oracle (projection-free): logits/offsets -> softmax/locations -> per-frame loop.
+    8 heads: the value-row size is a compile-time immediate of the dead-corner consumer; 3 heads: the run-time form."""
     from devis_b200 import TemporalMSDeformAttnFusedFunction, clip_geometry, synthetic
     from oracle import temporal_torch
     torch.manual_seed(1)
-    shapes_l, T, M, D, pc, pt = ((18, 30), (9, 15), (5, 8)), 4, 8, 32, 4, 4
+    shapes_l, T, D, pc, pt = ((18, 30), (9, 15), (5, 8)), 4, 32, 4, 4
     nl, wt = len(shapes_l), T - 1
     S = sum(h * w for h, w in shapes_l)
     geom = clip_geometry.ClipGeometry(shapes_l, T, clip_geometry.all_frames_table(T))
