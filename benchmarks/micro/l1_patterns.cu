@@ -118,6 +118,22 @@ __global__ void __launch_bounds__(1024) k(const float *__restrict__ g, float *ou
             const float4 *p = reinterpret_cast<const float4 *>(base + row * 128 + (lane & 3) * 32);
             const float4 v = __ldg(p), u = __ldg(p + 1);
             acc += v.x + v.y + v.z + v.w + u.x + u.y + u.z + u.w;
+        } else if (MODE >= 21 && MODE <= 24) {  // LDG.128 8 lanes/row with (MODE - 20) of the 4 lane groups predicated OFF
+            const unsigned row = ROW8;
+            float4 v = make_float4(acc, acc, acc, acc);
+            const unsigned live = gid8 >= (MODE - 20);       // groups 0 .. MODE-21 are dead
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                         : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                         : "l"(base + row * 128 + (lane & 7) * 16), "r"(live));
+            acc += v.x + v.y + v.z + v.w;
+        } else if (MODE == 25) {  // as 22 (two groups dead), but which two varies per iteration and warp
+            const unsigned row = ROW8;
+            float4 v = make_float4(acc, acc, acc, acc);
+            const unsigned live = ((s1 >> (12 + gid8)) & 1u);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                         : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                         : "l"(base + row * 128 + (lane & 7) * 16), "r"(live));
+            acc += v.x + v.y + v.z + v.w;
         } else if (MODE == 16) {  // LDG.128, 4 lanes x 16 B = 64 B contiguous per row, 8 rows (bf16, 8 ch / lane)
             const unsigned row = ROW4;
             const float4 v = __ldg(reinterpret_cast<const float4 *>(base + row * 128 + ((row & 1) ? 64 : 0)) + (lane & 3));
@@ -150,7 +166,7 @@ void run(const char *name, const float *g, float *out, float *red, long long *cy
 
 int main(int argc, char **argv)
 {
-    const bool red_only = argc > 1;
+    const bool red_only = argc > 1 && argv[1][0] != 'p';
     float *g, *out, *red;
     long long *cyc;
     const size_t n = (size_t)148 * ROWS * 32;
@@ -166,6 +182,17 @@ int main(int argc, char **argv)
             run<11>("RED.128  8 lanes/row, 4 rows", g, out, red, cyc, 1024);
             run<13>("RED.32   32 lanes, 1 row", g, out, red, cyc, 1024);
             run<0>("LDG.128  4 full rows (L1 hits)", g, out, red, cyc, 1024);
+        }
+        return 0;
+    }
+    if (argc > 1 && argv[1][0] == 'p') {        // ./l1_patterns p : predicated-off lane groups
+        for (int threads : {256, 1024}) {
+            run<0>("LDG.128  8 lanes/row, 4 live rows", g, out, red, cyc, threads);
+            run<21>("LDG.128  8 lanes/row, 3 live rows (group 0 predicated off)", g, out, red, cyc, threads);
+            run<22>("LDG.128  8 lanes/row, 2 live rows", g, out, red, cyc, threads);
+            run<23>("LDG.128  8 lanes/row, 1 live row", g, out, red, cyc, threads);
+            run<24>("LDG.128  8 lanes/row, 0 live rows (all predicated off)", g, out, red, cyc, threads);
+            run<25>("LDG.128  8 lanes/row, random half of the groups off", g, out, red, cyc, threads);
         }
         return 0;
     }
