@@ -726,9 +726,10 @@ def run_ours(args, rank, world, local_rank):
                           # since round 2 the forward gathers only the live corners; the figure above keeps round 1's
                           # definition (all 4 corners of every tap) so that rounds compare
                           "live_row_bytes": red_rows * row_bytes,
-                          "gather_instructions_per_sm": T_FRAMES * S_ROWS * HEADS * K_TAPS * 4 // 4 // sm_count,
+                          # one 128-bit gather instruction covers 4 rows (fp32, 8 lanes per row) or 8 (bf16, 4 lanes)
+                          "gather_instructions_per_sm": T_FRAMES * S_ROWS * HEADS * K_TAPS * 4 // (4 if elem == 4 else 8) // sm_count,
                           "cycles_per_gather_instruction": us_fwd * 1e-6 * sm_hz /
-                                                           (T_FRAMES * S_ROWS * HEADS * K_TAPS * 4 / 4 / sm_count)},
+                                                           (T_FRAMES * S_ROWS * HEADS * K_TAPS * 4 / (4 if elem == 4 else 8) / sm_count)},
         "bwd_reduction_egress": {"row_reductions": red_rows, "cycles_per_row": cycles_per_row,
                                  "busy_frac": red_rows / sm_count * cycles_per_row / (us_bwd * 1e-6 * sm_hz)},
         "sm_count": sm_count, "sm_mhz": sm_mhz,
