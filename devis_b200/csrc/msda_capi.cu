@@ -78,12 +78,6 @@ int devis_capi_check_launch(int family)
     return e == cudaSuccess ? DEVIS_MSDA_OK : devis_capi_cuda_fail(e);
 }
 
-#ifndef DEVIS_FWD_VIRTUAL
-#define DEVIS_FWD_VIRTUAL 1
-#endif
-#ifndef DEVIS_FWD_WIDE_F32
-#define DEVIS_FWD_WIDE_F32 0    // 1: fp32 value takes the four-lane x 8-channel shape too (A/B)
-#endif
 // compile-time A/B of the launch shape of msda_fwdv_kernel (benchmarks/build_variants.py); 0 = pick_shape decides
 #ifndef DEVIS_FWDV_THREADS
 #define DEVIS_FWDV_THREADS 0
@@ -150,100 +144,48 @@ int launch_forward(const FwdArgs<SlotSrc> &a, int dtype, cudaStream_t st)
     if (d.outer == 0 || d.Lq == 0) return DEVIS_MSDA_OK;
     size_t smem = (size_t)a.n_slots_total * sizeof(int4);
     const int lpg = lanes_per_group(dtype, d);
-    // D = 32 with P % 4 == 0 in every segment can use 4 lanes x 8 channels with 16-byte tap records
-    // (msda_fwd8_kernel).  Measured at the DeVIS shape: bf16 -10 % (64-B rows: 0.75 instead of 1.0 data-pipe cycles per
-    // row), fp32 +-1 % local / +10 % uniform taps (LDG.256 costs 1.18 wavefronts per 128-B row against 1.01 for
-    // LDG.128, which eats what the smaller tap record saves) -> default: bf16 only.  Tuning key 4: 1 never, 2 always.
-    const int wide_mode = g_tuning[4].load();
-    bool wide = lpg == 8 && (wide_mode == 2 || (wide_mode == 0 && (dtype == DEVIS_MSDA_BF16 || DEVIS_FWD_WIDE_F32)));
-    for (int sg = 0; sg < a.n_seg; ++sg) wide = wide && (a.seg[sg].P % 4 == 0);
-    if (wide) {
-        LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32, 2, 0, 1);
-        if (dtype != DEVIS_MSDA_BF16) {      // compile-time A/B of the fp32 launch shape (benchmarks/build_variants.py)
-            if (DEVIS_FWDV_THREADS && s.threads > DEVIS_FWDV_THREADS) s.threads = DEVIS_FWDV_THREADS;
-            if (DEVIS_FWDV_QPG && s.qpg > DEVIS_FWDV_QPG) s.qpg = DEVIS_FWDV_QPG;
-        }
+    // D = 32 with P % 4 == 0 in every segment and value below 2 GiB (signed 32-bit tap offsets): the round-2 kernels with
+    // 16-byte tap records and the dead corners skipped.  fp32 value: eight lanes x 4 channels (msda_fwdv_kernel); bf16
+    // value: four lanes x 8 channels (msda_fwd8v_kernel: 64-byte rows cost 0.75 instead of 1.0 data-pipe cycles that way;
+    // for fp32 the four-lane shape needs LDG.E.256 and loses, profiles/r2s_fwd_wide_f32_variants.json).  With 8 heads the
+    // size of a value row is a compile-time immediate of the gathers.  Everything else takes msda_fwd_kernel below.
+    bool compact = lpg == 8 && (unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31);
+    for (int sg = 0; sg < a.n_seg; ++sg) compact = compact && (a.seg[sg].P % 4 == 0);
+    if (compact && dtype == DEVIS_MSDA_BF16) {
+        const LaunchShape s = pick_shape(d.Lq, kShapeFwdBf16, 2, 0, 1);
         smem += (size_t)(s.threads / 32) * Tap16::kBytesPerWarp;
         const int qc = s.threads / 4;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
         if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
         const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
-#define DEVIS_FWD8(BF, QPG) msda_fwd8_kernel<BF, QPG, SlotSrc><<<grid, s.threads, smem, st>>>(a)
-#if DEVIS_FWD_VIRTUAL
-        // round 2: the four-lane shape with the dead corners skipped (msda_fwd8v_kernel); signed offsets -> value < 2 GiB
-        if ((unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31)) {
-#define DEVIS_FWD8V(BF, QPG)                                                                                  \
-    do {                                                                                                      \
-        if (d.M == 8) msda_fwd8v_kernel<BF, QPG, SlotSrc, (BF ? 512 : 1024)><<<grid, s.threads, smem, st>>>(a); \
-        else msda_fwd8v_kernel<BF, QPG, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);                        \
-    } while (0)
-            if (dtype == DEVIS_MSDA_BF16) {
-                if (s.qpg == 2) DEVIS_FWD8V(true, 2);
-                else DEVIS_FWD8V(true, 1);
-            } else {
-                if (s.qpg == 2) DEVIS_FWD8V(false, 2);
-                else DEVIS_FWD8V(false, 1);
-            }
-#undef DEVIS_FWD8V
-            return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
-        }
-#endif
-        if (dtype == DEVIS_MSDA_BF16) {
-            if (s.qpg == 2) DEVIS_FWD8(true, 2);
-            else DEVIS_FWD8(true, 1);
+        if (d.M == 8) {
+            if (s.qpg == 2) msda_fwd8v_kernel<2, SlotSrc, 512><<<grid, s.threads, smem, st>>>(a);
+            else msda_fwd8v_kernel<1, SlotSrc, 512><<<grid, s.threads, smem, st>>>(a);
         } else {
-            if (s.qpg == 2) DEVIS_FWD8(false, 2);
-            else DEVIS_FWD8(false, 1);
+            if (s.qpg == 2) msda_fwd8v_kernel<2, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);
+            else msda_fwd8v_kernel<1, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);
         }
-#undef DEVIS_FWD8
         return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
     }
-    // 8 lanes x 4 channels with 16-byte tap records (msda_fwdc_kernel), D = 32 and P % 4 == 0: -4..5 % against the
-    // 32-byte records for fp32 value (default for fp32).  Tuning key 5: 1 always, 2 never.
-    const int compact_mode = g_tuning[5].load();
-    bool compact = lpg == 8 && (compact_mode == 1 || (compact_mode == 0 && dtype == DEVIS_MSDA_F32));
-    for (int sg = 0; sg < a.n_seg; ++sg) compact = compact && (a.seg[sg].P % 4 == 0);
     if (compact) {
-        LaunchShape s = pick_shape(d.Lq, dtype == DEVIS_MSDA_BF16 ? kShapeFwdBf16 : kShapeFwdF32,
-                                   dtype == DEVIS_MSDA_BF16 ? 2 : 4, 0, 1);
-#if DEVIS_FWD_VIRTUAL
+        LaunchShape s = pick_shape(d.Lq, kShapeFwdF32, 4, 0, 1);
         if (DEVIS_FWDV_THREADS && s.threads > DEVIS_FWDV_THREADS) s.threads = DEVIS_FWDV_THREADS;
         if (DEVIS_FWDV_QPG && s.qpg > DEVIS_FWDV_QPG) s.qpg = DEVIS_FWDV_QPG;
         if (s.threads > DEVIS_FWDV_MAXT) s.threads = DEVIS_FWDV_MAXT;
-#endif
         smem += (size_t)(s.threads / 32) * Tap16x8::kBytesPerWarp;
         const int qc = s.threads / 8;
         const long long chunks = ((long long)d.Lq + (long long)qc * s.qpg - 1) / ((long long)qc * s.qpg);
         if (chunks * d.M > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
         const dim3 grid((unsigned)(chunks * d.M), (unsigned)d.outer);
-#if DEVIS_FWD_VIRTUAL
-        // round 2: dead corners skipped, virtual top-left addressing (msda_fwdv_kernel); signed offsets -> value < 2 GiB
-        if ((unsigned long long)d.outer * d.S * d.M * d.D * elem_size(dtype) < (1ull << 31)) {
-#define DEVIS_FWDV(BF, QPG)                                                                                \
-    do {                                                                                                   \
-        if (d.M == 8) msda_fwdv_kernel<BF, QPG, SlotSrc, (BF ? 512 : 1024)><<<grid, s.threads, smem, st>>>(a); \
-        else msda_fwdv_kernel<BF, QPG, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);                      \
+#define DEVIS_FWDV(QPG)                                                                              \
+    do {                                                                                             \
+        if (d.M == 8) msda_fwdv_kernel<false, QPG, SlotSrc, 1024><<<grid, s.threads, smem, st>>>(a); \
+        else msda_fwdv_kernel<false, QPG, SlotSrc, 0><<<grid, s.threads, smem, st>>>(a);             \
     } while (0)
-            if (dtype == DEVIS_MSDA_BF16) {
-                if (s.qpg == 2) DEVIS_FWDV(true, 2);
-                else DEVIS_FWDV(true, 1);
-            } else {
-                if (s.qpg == 4) DEVIS_FWDV(false, 4);
-                else if (s.qpg == 2) DEVIS_FWDV(false, 2);
-                else DEVIS_FWDV(false, 1);
-            }
+        if (s.qpg == 4) DEVIS_FWDV(4);
+        else if (s.qpg == 2) DEVIS_FWDV(2);
+        else DEVIS_FWDV(1);
 #undef DEVIS_FWDV
-            return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
-        }
-#endif
-        if (dtype == DEVIS_MSDA_BF16) {
-            if (s.qpg == 2) msda_fwdc_kernel<true, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
-            else msda_fwdc_kernel<true, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
-        } else {
-            if (s.qpg == 4) msda_fwdc_kernel<false, 4, SlotSrc><<<grid, s.threads, smem, st>>>(a);
-            else if (s.qpg == 2) msda_fwdc_kernel<false, 2, SlotSrc><<<grid, s.threads, smem, st>>>(a);
-            else msda_fwdc_kernel<false, 1, SlotSrc><<<grid, s.threads, smem, st>>>(a);
-        }
         return check_launch(DEVIS_MSDA_KERNEL_FWD_GROUPED);
     }
     if (lpg) {
@@ -746,22 +688,20 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
     dim3 grid;
     int threads;
     size_t smem;
-    // round 2: dead corners skipped, virtual top-left addressing (signed 32-bit offsets: value < 2 GiB; 8 heads: the row
-    // size is a compile-time constant); DEVIS_FWD_VIRTUAL=0 builds keep the round-1 consumer
-    const bool virt = DEVIS_FWD_VIRTUAL && (unsigned long long)num_frames * spatial_size * num_heads * channels *
-                                                   elem_size(dtype) < (1ull << 31);
-#define DEVIS_FUSED_FWD(QPG, GEN)                                                                                          \
-    do {                                                                                                                   \
-        cudaStream_t st_ = (cudaStream_t)stream;                                                                           \
-        if (dtype == DEVIS_MSDA_BF16) {                                                                                    \
-            if (virt && num_heads == 8) tmsda_fused_fwd_kernel<true, QPG, GEN, 512><<<grid, threads, smem, st_>>>(a);      \
-            else if (virt) tmsda_fused_fwd_kernel<true, QPG, GEN, 0><<<grid, threads, smem, st_>>>(a);                     \
-            else tmsda_fused_fwd_kernel<true, QPG, GEN, -1><<<grid, threads, smem, st_>>>(a);                              \
-        } else {                                                                                                           \
-            if (virt && num_heads == 8) tmsda_fused_fwd_kernel<false, QPG, GEN, 1024><<<grid, threads, smem, st_>>>(a);    \
-            else if (virt) tmsda_fused_fwd_kernel<false, QPG, GEN, 0><<<grid, threads, smem, st_>>>(a);                    \
-            else tmsda_fused_fwd_kernel<false, QPG, GEN, -1><<<grid, threads, smem, st_>>>(a);                             \
-        }                                                                                                                  \
+    // dead corners skipped, virtual top-left addressing: signed 32-bit offsets, so value must stay below 2 GiB (the Python
+    // side then uses the unfused op); with 8 heads the row size is a compile-time constant
+    if ((unsigned long long)num_frames * spatial_size * num_heads * channels * elem_size(dtype) >= (1ull << 31))
+        return DEVIS_MSDA_ERR_UNSUPPORTED;
+#define DEVIS_FUSED_FWD(QPG, GEN)                                                                                  \
+    do {                                                                                                           \
+        cudaStream_t st_ = (cudaStream_t)stream;                                                                   \
+        if (dtype == DEVIS_MSDA_BF16) {                                                                            \
+            if (num_heads == 8) tmsda_fused_fwd_kernel<true, QPG, GEN, 512><<<grid, threads, smem, st_>>>(a);      \
+            else tmsda_fused_fwd_kernel<true, QPG, GEN, 0><<<grid, threads, smem, st_>>>(a);                       \
+        } else {                                                                                                   \
+            if (num_heads == 8) tmsda_fused_fwd_kernel<false, QPG, GEN, 1024><<<grid, threads, smem, st_>>>(a);    \
+            else tmsda_fused_fwd_kernel<false, QPG, GEN, 0><<<grid, threads, smem, st_>>>(a);                      \
+        }                                                                                                          \
     } while (0)
     // the general (decoder) form: boxes, per-level / instance-aware temporal reference points, by-products
     const bool general = ref_dim == 4 || (a.n_seg > 1 && temporal_ref_mode != 0) || loc_curr_out || aw_curr_out ||
@@ -772,9 +712,8 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
         DEVIS_FUSED_FWD(1, true);
         return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
     }
-    // bf16 value: four lanes x 8 channels per (query, head) like msda_fwd8_kernel (tuning key 4: 1 never, 2 always)
-    const int wide_mode = g_tuning[4].load();
-    if (wide_mode == 2 || (wide_mode == 0 && dtype == DEVIS_MSDA_BF16)) {
+    // bf16 value: four lanes x 8 channels per (query, head) like msda_fwd8v_kernel
+    if (dtype == DEVIS_MSDA_BF16) {
         threads = g_tuning[0].load();
         if (threads == 0) threads = num_query >= 1024 ? 128 : 64;
         threads = threads < 32 ? 32 : threads > 256 ? 256 : (threads / 32) * 32;
@@ -782,15 +721,11 @@ int devis_tmsda_fused_forward(const void *value, const int64_t *spatial_shapes_h
         if (chunks * num_heads > 0x7fffffffLL) return DEVIS_MSDA_ERR_TOO_LARGE;
         grid = dim3((unsigned)(chunks * num_heads), (unsigned)num_frames);
         smem = (size_t)(a.n_slots[0] + a.n_slots[1]) * sizeof(int4) + (size_t)(threads / 32) * Tap16::kBytesPerWarp;
-        if (dtype == DEVIS_MSDA_BF16 && virt && num_heads == 8)
-            tmsda_fused_fwd8_kernel<true, 512><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        else if (dtype == DEVIS_MSDA_BF16 && virt)
-            tmsda_fused_fwd8_kernel<true, 0><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        else if (dtype == DEVIS_MSDA_BF16) tmsda_fused_fwd8_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-        else tmsda_fused_fwd8_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        if (num_heads == 8) tmsda_fused_fwd8_kernel<512><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        else tmsda_fused_fwd8_kernel<0><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
         return check_launch(DEVIS_MSDA_KERNEL_FUSED_FWD);
     }
-    // two queries per lane group for fp32 at encoder sizes, like msda_fwdc_kernel (tuning key 1 overrides)
+    // two queries per lane group for fp32 at encoder sizes, like msda_fwdv_kernel (tuning key 1 overrides)
     int qpg = g_tuning[1].load();
     if (qpg != 1 && qpg != 2) qpg = (dtype == DEVIS_MSDA_F32 && num_query >= 2048) ? 2 : 1;
     rc = fused_grid(a, 0, grid, threads, smem, qpg);

@@ -19,7 +19,6 @@
 // temporal op (SlotSrc = ClipTable, two segments, value indexed through the frame table).
 #pragma once
 #include "msda_common.cuh"
-#include <type_traits>
 
 #ifndef DEVIS_FWD_TAP_BATCH
 #define DEVIS_FWD_TAP_BATCH 2
@@ -154,9 +153,7 @@ __global__ void __launch_bounds__(256, DEVIS_FWD_MIN_BLOCKS) msda_fwd_kernel(con
 
 
 // =================================================================================================
-// msda_fwdc_kernel -- D = 32, EIGHT lanes per (query, head) like msda_fwd_kernel, but with the 16-byte tap
-// record of msda_fwd8_kernel (one LDS.128 per tap instead of two).  An exchange covers 8 taps = two aligned groups
-// of 4, each inside one slot (P % 4 == 0), so the two row pitches a consumer needs come from two shuffles per exchange.
+// Exchange layout of the 16-byte tap records, eight taps x four lane groups per warp and buffer
 // =================================================================================================
 struct Tap16x8 {
     static constexpr int kWordsPerWarpBuf = 8 * 4 * 4;  // 8 taps x 4 groups x 4 words
@@ -166,170 +163,14 @@ struct Tap16x8 {
     __device__ static __forceinline__ int word(int j, int g) { return (j * 4 + (g ^ (j & 3))) * 4; }
 };
 
-
-// 16-byte tap record shared by msda_fwdc_kernel, msda_fwd8_kernel and the fused-prologue forward
-__device__ __forceinline__ uint4 make_tap16(const TapGeom &t, float w, unsigned rowbytes)
-{
-    uint4 rec;
-    rec.x = (unsigned)t.rTL * rowbytes | (unsigned)(t.rTR != t.rTL) | ((unsigned)(t.rBL != t.rTL) << 1) | (t.ok & 4u) |
-            (t.ok & 8u);
-    rec.y = __float_as_uint((t.ok & 1u) ? w * t.hh : 0.f);
-    rec.z = __float_as_uint((t.ok & 2u) ? w * t.lh : 0.f);
-    rec.w = __float_as_uint(t.lw);
-    return rec;
-}
-
-__device__ __forceinline__ void decode_tap16(const uint4 r, unsigned rowbytes, unsigned pitch, unsigned (&o)[4], float (&c)[4])
-{
-    const unsigned dcol = (r.x & 1u) ? rowbytes : 0u, drow = (r.x & 2u) ? pitch : 0u;
-    o[0] = r.x & ~15u;
-    o[1] = o[0] + dcol;
-    o[2] = o[0] + drow;
-    o[3] = o[2] + dcol;
-    const float lw = __uint_as_float(r.w);
-    const float hwm = (r.x & 4u) ? 1.f - lw : 0.f, lwm = (r.x & 8u) ? lw : 0.f;
-    const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
-    c[0] = whh * hwm;
-    c[1] = whh * lwm;
-    c[2] = wlh * hwm;
-    c[3] = wlh * lwm;
-}
-
-// one exchange of 8 published records -> 32 corner gathers and 128 FFMA per lane (8 lanes x 4 channels per row)
-template <bool BF16>
-__device__ __forceinline__ void consume_tap16x8(const float *buf, int g, unsigned rowbytes, unsigned pitch_lo,
-                                                unsigned pitch_hi, const char *vbase, float4 &acc, const L2Policy &pol)
-{
-#pragma unroll
-    for (int j0 = 0; j0 < 8; j0 += 2) {
-        unsigned o[2][4];
-        float c[2][4];
-        float4 v[2][4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-            decode_tap16(*reinterpret_cast<const uint4 *>(buf + Tap16x8::word(j0 + u, g)), rowbytes,
-                         (j0 + u) < 4 ? pitch_lo : pitch_hi, o[u], c[u]);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                v[u][e] = BF16 ? ldg_bf16x4(reinterpret_cast<const uint2 *>(vbase + o[u][e]))
-                               : ldg_f4(reinterpret_cast<const float4 *>(vbase + o[u][e]), pol);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            acc.x = fmaf(c[u][3], v[u][3].x, fmaf(c[u][2], v[u][2].x, fmaf(c[u][1], v[u][1].x, fmaf(c[u][0], v[u][0].x, acc.x))));
-            acc.y = fmaf(c[u][3], v[u][3].y, fmaf(c[u][2], v[u][2].y, fmaf(c[u][1], v[u][1].y, fmaf(c[u][0], v[u][0].y, acc.y))));
-            acc.z = fmaf(c[u][3], v[u][3].z, fmaf(c[u][2], v[u][2].z, fmaf(c[u][1], v[u][1].z, fmaf(c[u][0], v[u][0].z, acc.z))));
-            acc.w = fmaf(c[u][3], v[u][3].w, fmaf(c[u][2], v[u][2].w, fmaf(c[u][1], v[u][1].w, fmaf(c[u][0], v[u][0].w, acc.w))));
-        }
-    }
-}
-
-template <bool BF16, int QPG, class SlotSrc>
-__global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc> a)
-{
-    constexpr int LPG = 8;
-    extern __shared__ int4 s_slot[];
-    const int outer = blockIdx.y;
-    build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
-    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16x8::kWordsPerWarpBuf);
-
-    const int M = a.d.M, Lq = a.d.Lq;
-    const int j = threadIdx.x & 7, g = (threadIdx.x & 31) >> 3, grp = threadIdx.x >> 3, QC = blockDim.x >> 3;
-    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
-    const L2Policy pol = make_l2_policy();
-
-    int q[QPG];
-    bool qlive[QPG];
-#pragma unroll
-    for (int i = 0; i < QPG; ++i) {
-        const int qi = (qchunk * QPG + i) * QC + grp;
-        qlive[i] = qi < Lq;
-        q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
-    }
-
-    constexpr unsigned kQuadBytes = BF16 ? 8u : 16u;
-    const unsigned rowbytes = (unsigned)(M * LPG) * kQuadBytes;
-    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kQuadBytes;
-    asm volatile("" : "+l"(vbase));
-
-    float4 acc[QPG];
-#pragma unroll
-    for (int i = 0; i < QPG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // The (location, weight) operands stream from HBM: the loads of exchange e+1 are issued BEFORE exchange e is
-    // consumed, so their DRAM latency hides under 32 corner gathers (round-1f profile: 9 % of all warp stall samples
-    // sat on the first use of an un-prefetched location).
-    struct TapIn {
-        float2 xy;
-        float w;
-    };
-    auto load_taps = [&](int sg, int k0, TapIn (&in)[QPG]) {
-        const int K = a.seg[sg].n_slots * a.seg[sg].P;
-        const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
-        const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
-        const int k = k0 + j;
-#pragma unroll
-        for (int i = 0; i < QPG; ++i) {
-            const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
-            in[i].xy = make_float2(0.f, 0.f);
-            in[i].w = 0.f;
-            if (k < K && qlive[i]) {
-                in[i].xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k, pol);
-                in[i].w = ld_stream_f(aw + row * K + k, pol);
-            }
-        }
-    };
-
-    int slot_base = 0, parity = 0;
-    TapIn nxt[QPG];
-    load_taps(0, 0, nxt);
-    for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);   // P % 4 == 0, hence K % 4 == 0
-        for (int k0 = 0; k0 < K; k0 += LPG) {
-            const int k = k0 + j;
-            const bool klive = k < K;
-            const int4 sl = s_slot[slot_base + (klive ? div_p(k, P, pshift) : 0)];
-            const unsigned my_pitch = (unsigned)sl.y * rowbytes;
-            const unsigned pitch_lo = __shfl_sync(0xffffffffu, my_pitch, 0, 8);   // slot of taps k0 .. k0+3
-            const unsigned pitch_hi = __shfl_sync(0xffffffffu, my_pitch, 4, 8);   // slot of taps k0+4 .. k0+7
-            TapIn cur[QPG];
-#pragma unroll
-            for (int i = 0; i < QPG; ++i) cur[i] = nxt[i];
-            if (k0 + LPG < K) load_taps(sg, k0 + LPG, nxt);
-            else if (sg + 1 < a.n_seg) load_taps(sg + 1, 0, nxt);
-#pragma unroll
-            for (int i = 0; i < QPG; ++i) {
-                const bool live = klive && qlive[i];
-                const TapGeom t = tap_geometry(cur[i].xy.x, cur[i].xy.y, sl, live);
-                float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
-                parity ^= 1;
-                *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, cur[i].w, rowbytes);
-                __syncwarp();
-                consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], pol);
-            }
-        }
-        slot_base += a.seg[sg].n_slots;
-    }
-
-#pragma unroll
-    for (int i = 0; i < QPG; ++i) {
-        if (!qlive[i]) continue;
-        const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
-        if (BF16)
-            reinterpret_cast<uint2 *>(a.out)[row * LPG + j] = pack_bf16x4(acc[i]);
-        else
-            st_stream_f4(reinterpret_cast<float4 *>(a.out) + row * LPG + j, acc[i], pol);
-    }
-}
-
 // =================================================================================================
-// msda_fwdv_kernel (round 2) -- msda_fwdc_kernel with DEAD CORNERS SKIPPED and a cheaper consumer.
+// msda_fwdv_kernel (round 2; default for D = 32, P % 4 == 0) -- eight lanes per (query, head) like msda_fwd_kernel, ONE
+// 16-byte record per tap (one LDS.128 instead of two), operands prefetched one exchange ahead, DEAD CORNERS SKIPPED.
 //   record = { signed byte offset of the footprint's top-left cell | 4 live bits,  w*hh,  w*lh,  lw }
 // (tap_geometry_v).  The consumer forms TL = base + offset and BL = TL + map-row pitch (two 64-bit adds); TR and BR are
 // the same two registers with an IMMEDIATE of one value row when the row size is a compile-time constant (ROWB: 8 heads
 // x 32 channels = 1024 B fp32 / 512 B bf16 -- every DeVIS configuration), so a tap costs 4 address instructions
-// instead of 8 and none of the clamp / mask selects of decode_tap16.  The four gathers and their 16 FFMA are predicated
+// instead of 8 and none of the clamp / mask selects the zero-factor form needs.  The four gathers and their 16 FFMA are predicated
 // on the live bits: a corner outside its map costs no L1 wavefront (28 % of all corners at the DeVIS layer-clip, where
 // most taps into the 6 x 10 and 12 x 20 maps of the other frames leave the map) and, unlike the zero-factor form, can
 // not leak a non-finite value of a neighbouring pixel into the result.  Offsets are signed 32-bit: value < 2 GiB.
@@ -345,7 +186,7 @@ __global__ void __launch_bounds__(256, 3) msda_fwdc_kernel(const FwdArgs<SlotSrc
 #endif
 // Predicated gather / accumulate as straight-line PTX: written as C++ `if (live) v = load; ... if (live) acc += c * v;`
 // the front end merges the two regions and the load is followed at once by its first use -- one gather in flight per
-// warp.  As PTX the eight gathers of a tap pair are issued back to back like the unpredicated ones of msda_fwdc_kernel.
+// warp.  As PTX the gathers of a tap (pair) are issued back to back like unpredicated ones.
 // A predicated-off gather keeps the previous content of its destination ("+f": ptxas treats a predicated write as a
 // read-modify-write anyway, and with write-only operands it kept all 128 destinations of an exchange live from kernel
 // entry -- 1.4 KB of spills); the 32 destination registers therefore live in the kernel's scope, zeroed once.  Only the
@@ -527,21 +368,10 @@ __global__ void __launch_bounds__(DEVIS_FWDV_MAXT, DEVIS_FWDV_MIN_BLOCKS) msda_f
 }
 
 // =================================================================================================
-// msda_fwd8_kernel -- D = 32 only: FOUR lanes per (query, head), 8 channels per lane.
-//
-// Round-1b profile + benchmarks/micro/l1_patterns.cu: the forward is bound by the SM's L1/shared data
-// pipe.  A gathered value row costs ~1.05 cycles however it is fetched (LDG.128 x 8 lanes, LDG.256 x 4
-// lanes, or LDS from a staged tile), so the only reducible cost is handing a tap's geometry to the lanes
-// that own its channels: every 32-bit word broadcast to a warp (SHFL or LDS) is one data-pipe wavefront.
-// This kernel halves the consumers per tap (4 lanes, 256-bit loads -- LDG.E.256 is new on sm_100) and
-// shrinks the record to ONE 16-byte LDS.128:  { TL byte offset | 4 flag bits,  w*hh,  w*lh,  lw }.
-//   flags: bit0 right column is a distinct row (else clamped onto the left one), bit1 bottom row distinct,
-//          bit2 left column inside the map, bit3 right column inside the map;
-//   hw = 1 - lw is recomputed (bit-identical to the producer's), the other three corner offsets follow
-//   from TL, the flags and the slot's row pitch.  Requires P % 4 == 0 so that the 4 taps a group
-//   exchanges at a time belong to one slot (DeVIS: P = 4 everywhere, config.py:52-53,108-109).
-// For bf16 value a head's row is 64 B = 4 lanes x 16 B: 8 rows per LDG.128, measured 0.75 cycles/row
-// against 1.0 for the 8-lane x 8-byte mapping.
+// Four lanes per (query, head), 8 channels per lane: the shape of the bf16 forward.  A head's bf16 row is 64 B = 4 lanes
+// x 16 B, 8 rows per LDG.128 (measured 0.75 data-pipe cycles per row against 1.0 for 8 lanes x 8 bytes), and the record
+// shrinks the exchange to ONE LDS.128 per tap for 8 groups.  Requires P % 4 == 0 so that the 4 taps a group exchanges at a
+// time belong to one slot (DeVIS: P = 4 everywhere, config.py:52-53,108-109).
 // =================================================================================================
 struct Tap16 {
     static constexpr int kWordsPerWarpBuf = 4 * 8 * 4;  // 4 taps x 8 groups x 4 words
@@ -549,148 +379,8 @@ struct Tap16 {
     __device__ static __forceinline__ int word(int j, int g) { return (j * 8 + (g ^ (2 * j))) * 4; }
 };
 
-__device__ __forceinline__ void ldg_f8(const char *p, float (&v)[8])
-{
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
-
-__device__ __forceinline__ void ldg_bf16x8(const char *p, float (&v)[8])
-{
-    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
-    v[0] = __uint_as_float(r.x << 16);
-    v[1] = __uint_as_float(r.x & 0xffff0000u);
-    v[2] = __uint_as_float(r.y << 16);
-    v[3] = __uint_as_float(r.y & 0xffff0000u);
-    v[4] = __uint_as_float(r.z << 16);
-    v[5] = __uint_as_float(r.z & 0xffff0000u);
-    v[6] = __uint_as_float(r.w << 16);
-    v[7] = __uint_as_float(r.w & 0xffff0000u);
-}
-
-// one exchange of 4 published records (4 lanes x 8 channels per row) -> 16 corner gathers and 128 FFMA per lane
-template <bool BF16>
-__device__ __forceinline__ void consume_tap16x4(const float *buf, int g, unsigned rowbytes, unsigned pitch,
-                                                const char *vbase, float (&acc)[8])
-{
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
-        const unsigned oTL = r.x & ~15u;
-        const unsigned dcol = (r.x & 1u) ? rowbytes : 0u, drow = (r.x & 2u) ? pitch : 0u;
-        const unsigned oTR = oTL + dcol, oBL = oTL + drow, oBR = oBL + dcol;
-        const float lw = __uint_as_float(r.w);
-        const float hwm = (r.x & 4u) ? 1.f - lw : 0.f, lwm = (r.x & 8u) ? lw : 0.f;
-        const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
-        const float c00 = whh * hwm, c01 = whh * lwm, c10 = wlh * hwm, c11 = wlh * lwm;
-        float v00[8], v01[8], v10[8], v11[8];
-        if (BF16) {
-            ldg_bf16x8(vbase + oTL, v00);
-            ldg_bf16x8(vbase + oTR, v01);
-            ldg_bf16x8(vbase + oBL, v10);
-            ldg_bf16x8(vbase + oBR, v11);
-        } else {
-            ldg_f8(vbase + oTL, v00);
-            ldg_f8(vbase + oTR, v01);
-            ldg_f8(vbase + oBL, v10);
-            ldg_f8(vbase + oBR, v11);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            acc[c] = fmaf(c11, v11[c], fmaf(c10, v10[c], fmaf(c01, v01[c], fmaf(c00, v00[c], acc[c]))));
-    }
-}
-
-template <bool BF16, int QPG, class SlotSrc>
-__global__ void __launch_bounds__(256) msda_fwd8_kernel(const FwdArgs<SlotSrc> a)
-{
-    constexpr int LPG = 4;
-    extern __shared__ int4 s_slot[];
-    const int outer = blockIdx.y;
-    build_slots(s_slot, a.src, a.d, outer, a.n_slots_total);
-    float *xbuf = reinterpret_cast<float *>(s_slot + a.n_slots_total) + (threadIdx.x >> 5) * (2 * Tap16::kWordsPerWarpBuf);
-
-    const int M = a.d.M, Lq = a.d.Lq;
-    const int j = threadIdx.x & 3;            // 8-channel slice owned by this lane == tap it prepares
-    const int g = (threadIdx.x & 31) >> 2;    // group within the warp (8 groups)
-    const int grp = threadIdx.x >> 2;         // group within the CTA
-    const int QC = blockDim.x >> 2;
-    const int qchunk = blockIdx.x / M, m = blockIdx.x - qchunk * M;
-
-    int q[QPG];
-    bool qlive[QPG];
-#pragma unroll
-    for (int i = 0; i < QPG; ++i) {
-        const int qi = (qchunk * QPG + i) * QC + grp;
-        qlive[i] = qi < Lq;
-        q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
-    }
-
-    constexpr unsigned kLaneBytes = BF16 ? 16u : 32u;      // 8 channels
-    const unsigned rowbytes = (unsigned)(M * LPG) * kLaneBytes;
-    const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kLaneBytes;
-    asm volatile("" : "+l"(vbase));   // keep base as one 64-bit register pair (see msda_fwd_kernel)
-
-    float acc[QPG][8];
-#pragma unroll
-    for (int i = 0; i < QPG; ++i)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
-
-    int slot_base = 0, parity = 0;
-    for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int P = a.seg[sg].P, K = a.seg[sg].n_slots * P, pshift = pow2_shift(P);   // P % 4 == 0 (checked by the launcher)
-        const float *loc = reinterpret_cast<const float *>(a.seg[sg].loc);
-        const float *aw = reinterpret_cast<const float *>(a.seg[sg].aw);
-        for (int k0 = 0; k0 < K; k0 += LPG) {
-            const int k = k0 + j;                                // always < K
-            const int4 sl = s_slot[slot_base + div_p(k0, P, pshift)];          // one slot for the whole exchange
-            const unsigned pitch = (unsigned)sl.y * rowbytes;    // bytes between vertically adjacent rows
-#pragma unroll
-            for (int i = 0; i < QPG; ++i) {
-                const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
-                float2 xy = make_float2(0.f, 0.f);
-                float w = 0.f;
-                if (qlive[i]) {
-                    xy = ld_stream_f2(reinterpret_cast<const float2 *>(loc + row * K * 2) + k);
-                    w = ld_stream_f(aw + row * K + k);
-                }
-                const TapGeom t = tap_geometry(xy.x, xy.y, sl, qlive[i]);
-                uint4 rec;
-                rec.x = (unsigned)t.rTL * rowbytes | (unsigned)(t.rTR != t.rTL) | ((unsigned)(t.rBL != t.rTL) << 1) |
-                        (t.ok & 4u) | (t.ok & 8u);
-                rec.y = __float_as_uint((t.ok & 1u) ? w * t.hh : 0.f);
-                rec.z = __float_as_uint((t.ok & 2u) ? w * t.lh : 0.f);
-                rec.w = __float_as_uint(t.lw);
-                float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
-                parity ^= 1;
-                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = rec;
-                __syncwarp();
-                consume_tap16x4<BF16>(buf, g, rowbytes, pitch, vbase, acc[i]);
-            }
-        }
-        slot_base += a.seg[sg].n_slots;
-    }
-
-#pragma unroll
-    for (int i = 0; i < QPG; ++i) {
-        if (!qlive[i]) continue;
-        const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
-        if (BF16) {
-            const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-            const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
-            reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-            float4 *o = reinterpret_cast<float4 *>(a.out) + (row * LPG + j) * 2;
-            o[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            o[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-        }
-    }
-}
-
 // =================================================================================================
-// msda_fwd8v_kernel (round 2) -- msda_fwd8_kernel for bf16 value with the dead corners skipped: the record and the
+// msda_fwd8v_kernel (round 2; default for bf16 value) -- that shape with the dead corners skipped: the record and the
 // addressing of msda_fwdv_kernel (virtual top-left cell, live bits, row size as an immediate), four lanes x 8 channels per
 // (query, head), 16-byte gathers predicated on the live bits.  The bf16 forward is the kernel closest to the data-pipe
 // limit (87 % busy), so the 28 % of rows that need not be fetched show up in the time.
@@ -716,45 +406,6 @@ __device__ __forceinline__ void fma8_bf16_if(float (&acc)[8], float c, const uin
         : "f"(c), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7), "r"(live));
 }
 
-// fp32 value, 8 channels per lane: one predicated 32-byte gather (LDG.E.256)
-struct F8 {
-    float f[8];
-};
-__device__ __forceinline__ void ldg_f8_if(F8 &v, const char *p, unsigned live)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t@p ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
-        : "+f"(v.f[0]), "+f"(v.f[1]), "+f"(v.f[2]), "+f"(v.f[3]), "+f"(v.f[4]), "+f"(v.f[5]), "+f"(v.f[6]), "+f"(v.f[7])
-        : "l"(p), "r"(live));
-}
-__device__ __forceinline__ void fma8_if(float (&acc)[8], float c, const F8 &v, unsigned live)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %17, 0;\n\t"
-        "@p fma.rn.f32 %0, %8, %9, %0;\n\t@p fma.rn.f32 %1, %8, %10, %1;\n\t@p fma.rn.f32 %2, %8, %11, %2;\n\t"
-        "@p fma.rn.f32 %3, %8, %12, %3;\n\t@p fma.rn.f32 %4, %8, %13, %4;\n\t@p fma.rn.f32 %5, %8, %14, %5;\n\t"
-        "@p fma.rn.f32 %6, %8, %15, %6;\n\t@p fma.rn.f32 %7, %8, %16, %7;\n\t}"
-        : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
-        : "f"(c), "f"(v.f[0]), "f"(v.f[1]), "f"(v.f[2]), "f"(v.f[3]), "f"(v.f[4]), "f"(v.f[5]), "f"(v.f[6]), "f"(v.f[7]), "r"(live));
-}
-template <int ROWB>
-__device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch,
-                                                 const char *vbase, float (&acc)[8], F8 (&v)[4])
-{
-    const unsigned rowb = ROWB ? (unsigned)ROWB : rowbytes_rt;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        const uint4 r = *reinterpret_cast<const uint4 *>(buf + Tap16::word(jj, g));
-        const char *pt = vbase + (ptrdiff_t)(int)(r.x & ~15u);
-        const char *pb = pt + pitch;
-        const float lw = __uint_as_float(r.w), hw = 1.f - lw;
-        const float whh = __uint_as_float(r.y), wlh = __uint_as_float(r.z);
-        const float c[4] = {whh * hw, whh * lw, wlh * hw, wlh * lw};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) ldg_f8_if(v[e], ((e & 2) ? pb : pt) + ((e & 1) ? rowb : 0u), r.x & (1u << e));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) fma8_if(acc, c[e], v[e], r.x & (1u << e));
-    }
-}
-
 // one exchange of 4 published records (4 lanes x 8 bf16 channels per row), dead corners skipped
 template <int ROWB>
 __device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsigned rowbytes_rt, unsigned pitch,
@@ -776,13 +427,11 @@ __device__ __forceinline__ void consume_tap16x4v(const float *buf, int g, unsign
     }
 }
 
-// (bf16: NO minimum-blocks hint (0): ptxas settles at 62 registers, 359 us; a hint of 1 makes it unroll to 184 registers and 711 us,
-// a hint of 4 (64-register cap) gives 371 us)
-#ifndef DEVIS_FWD8V_F32_MIN_BLOCKS
-#define DEVIS_FWD8V_F32_MIN_BLOCKS 2
-#endif
-template <bool BF16, int QPG, class SlotSrc, int ROWB>
-__global__ void __launch_bounds__(256, BF16 ? 0 : DEVIS_FWD8V_F32_MIN_BLOCKS) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
+// (no minimum-blocks hint: ptxas settles at 62-64 registers, 359 us; a hint of 1 made it unroll to 184 registers and 711 us.
+// The fp32 form of this shape -- 32-byte predicated gathers, LDG.E.256 -- was measured at 527-543 us against 478 us for
+// msda_fwdv_kernel and is not kept, profiles/r2s_fwd_wide_f32_variants.json)
+template <int QPG, class SlotSrc, int ROWB>
+__global__ void __launch_bounds__(256) msda_fwd8v_kernel(const FwdArgs<SlotSrc> a)
 {
     constexpr int LPG = 4;
     extern __shared__ int4 s_slot[];
@@ -803,7 +452,7 @@ __global__ void __launch_bounds__(256, BF16 ? 0 : DEVIS_FWD8V_F32_MIN_BLOCKS) ms
         q[i] = qlive[i] ? (a.q_perm ? a.q_perm[qi] : qi) : 0;
     }
 
-    constexpr unsigned kLaneBytes = BF16 ? 16u : 32u;          // 8 channels
+    constexpr unsigned kLaneBytes = 16u;                       // 8 bf16 channels
     const unsigned rowbytes = ROWB ? (unsigned)ROWB : (unsigned)(M * LPG) * kLaneBytes;
     const char *vbase = reinterpret_cast<const char *>(a.value) + (size_t)(m * LPG + j) * kLaneBytes;
     asm volatile("" : "+l"(vbase));
@@ -813,10 +462,9 @@ __global__ void __launch_bounds__(256, BF16 ? 0 : DEVIS_FWD8V_F32_MIN_BLOCKS) ms
     for (int i = 0; i < QPG; ++i)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
-    // gather destinations (see ldg_f4_if): raw bf16x8 or eight floats per corner
-    typename std::conditional<BF16, uint4, F8>::type v[4];
+    uint4 v[4];                                                // gather destinations (see ldg_f4_if): raw bf16x8 per corner
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = {};
+    for (int e = 0; e < 4; ++e) v[e] = make_uint4(0u, 0u, 0u, 0u);
 
     int slot_base = 0, parity = 0;
     for (int sg = 0; sg < a.n_seg; ++sg) {
@@ -851,15 +499,9 @@ __global__ void __launch_bounds__(256, BF16 ? 0 : DEVIS_FWD8V_F32_MIN_BLOCKS) ms
     for (int i = 0; i < QPG; ++i) {
         if (!qlive[i]) continue;
         const size_t row = ((size_t)outer * Lq + q[i]) * M + m;
-        if (BF16) {
-            const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-            const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
-            reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-            float4 *o = reinterpret_cast<float4 *>(a.out) + (row * LPG + j) * 2;
-            st_stream_f4(o, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-            st_stream_f4(o + 1, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
-        }
+        const uint2 lo = pack_bf16x4(make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        const uint2 hi = pack_bf16x4(make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+        reinterpret_cast<uint4 *>(a.out)[row * LPG + j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
 }
 

@@ -183,8 +183,8 @@ __device__ __forceinline__ void raw_to_operands(const FusedArgs &a, int sg, cons
     w = expf(r.lg - rmax) * rinv;
 }
 
-// ROWB: -1 = clamped corners with zero factors (round 1); >= 0 = dead corners skipped, virtual top-left addressing
-// (consume_tap16v, msda_fwd.cuh; 0: row size at run time, else bytes of one value row)
+// Dead corners skipped, virtual top-left addressing (consume_tap16v, msda_fwd.cuh); ROWB: bytes of one value row as a
+// compile-time constant, 0 = known at run time only.  Signed offsets: value < 2 GiB (the launcher refuses larger ones).
 // measured (round 2, fused-prologue forward at the DeVIS layer-clip): 2 taps in flight at 2 blocks per SM 580 us, 1 tap
 // at 2 / 3 blocks 605 / 595 us -- the opposite of msda_fwdv_kernel (1 tap, 3 blocks: 480 us against 489 us)
 #ifndef DEVIS_FUSED_FWD_MIN_BLOCKS
@@ -193,8 +193,8 @@ __device__ __forceinline__ void raw_to_operands(const FusedArgs &a, int sg, cons
 #ifndef DEVIS_FUSED_FWD_TB
 #define DEVIS_FUSED_FWD_TB 2
 #endif
-template <bool BF16, int QPG, bool GEN = false, int ROWB = -1>
-__global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 3) tmsda_fused_fwd_kernel(const FusedArgs a)
+template <bool BF16, int QPG, bool GEN = false, int ROWB = 0>
+__global__ void __launch_bounds__(256, DEVIS_FUSED_FWD_MIN_BLOCKS) tmsda_fused_fwd_kernel(const FusedArgs a)
 {
     constexpr int LPG = 8;
     extern __shared__ int4 s_slot[];
@@ -271,17 +271,10 @@ __global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 
                 }
                 float *buf = xbuf + parity * Tap16x8::kWordsPerWarpBuf;
                 parity ^= 1;
-                if (ROWB >= 0) {
-                    const TapGeomV t = tap_geometry_v(x, y, sl, live);
-                    *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16v(t, w, rowbytes);
-                    __syncwarp();
-                    consume_tap16v<BF16, (ROWB > 0 ? ROWB : 0), DEVIS_FUSED_FWD_TB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
-                } else {
-                    const TapGeom t = tap_geometry(x, y, sl, live);
-                    *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16(t, w, rowbytes);
-                    __syncwarp();
-                    consume_tap16x8<BF16>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], pol);
-                }
+                const TapGeomV t = tap_geometry_v(x, y, sl, live);
+                *reinterpret_cast<uint4 *>(buf + Tap16x8::word(j, g)) = make_tap16v(t, w, rowbytes);
+                __syncwarp();
+                consume_tap16v<BF16, ROWB, DEVIS_FUSED_FWD_TB>(buf, g, rowbytes, pitch_lo, pitch_hi, vbase, acc[i], v);
             }
         }
         slot_base += a.n_slots[sg];
@@ -298,11 +291,11 @@ __global__ void __launch_bounds__(256, ROWB >= 0 ? DEVIS_FUSED_FWD_MIN_BLOCKS : 
 
 // Four lanes per (query, head), 8 channels per lane (msda_fwd8_kernel's shape): the forward of choice for bf16 value,
 // whose 64-byte rows cost 0.75 instead of 1.0 data-pipe cycles when 4 lanes fetch 16 bytes each.
-// ROWB >= 0 (bf16 value only): dead corners skipped, consume_tap16x4v; -1: round-1 consumer
-template <bool BF16, int ROWB = -1>
+// bf16 value only (the fp32 form of this shape loses to the eight-lane kernel); dead corners skipped, consume_tap16x4v
+template <int ROWB>
 __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a)
 {
-    static_assert(ROWB < 0 || BF16, "the dead-corner consumer of the 4-lane shape is bf16 only");
+    constexpr bool BF16 = true;
     constexpr int LPG = 4;
     extern __shared__ int4 s_slot[];
     const int outer = blockIdx.y, n_slots_total = a.n_slots[0] + (a.n_seg > 1 ? a.n_slots[1] : 0);
@@ -346,17 +339,10 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
             if (qlive) raw_to_operands<false>(a, sg, cur, sl, rmax, rinv, x, y, w);
             float *buf = xbuf + parity * Tap16::kWordsPerWarpBuf;
             parity ^= 1;
-            if (ROWB >= 0) {
-                const TapGeomV t = tap_geometry_v(x, y, sl, qlive);
-                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16v(t, w, rowbytes);
-                __syncwarp();
-                consume_tap16x4v<(ROWB > 0 ? ROWB : 0)>(buf, g, rowbytes, pitch, vbase, acc, v);
-            } else {
-                const TapGeom t = tap_geometry(x, y, sl, qlive);
-                *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16(t, w, rowbytes);
-                __syncwarp();
-                consume_tap16x4<BF16>(buf, g, rowbytes, pitch, vbase, acc);
-            }
+            const TapGeomV t = tap_geometry_v(x, y, sl, qlive);
+            *reinterpret_cast<uint4 *>(buf + Tap16::word(j, g)) = make_tap16v(t, w, rowbytes);
+            __syncwarp();
+            consume_tap16x4v<ROWB>(buf, g, rowbytes, pitch, vbase, acc, v);
         }
         slot_base += a.n_slots[sg];
     }

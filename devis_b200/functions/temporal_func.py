@@ -138,7 +138,7 @@ class TemporalMSDeformAttnFusedFunction(Function):
         """`value`: the projected value tensor (T,S,M,D) (or any tensor with its device, dtype and shape)"""
         return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16) and value.shape[-1] == 32
                 and n_curr_points % 4 == 0 and n_temporal_points % 4 == 0
-                and reference_points.shape[-1] in (2, 4) and value.numel() * value.element_size() < (1 << 32)
+                and reference_points.shape[-1] in (2, 4) and value.numel() * value.element_size() < (1 << 31)
                 # deterministic mode: grad_value goes through fixed point inside the kernel; d/d(reference points) is a
                 # float-atomic sum there, so learnable reference points take the unfused path in that mode
                 and not (MSDA.deterministic_enabled(value.dtype) and reference_points.requires_grad))

@@ -87,8 +87,7 @@ uint64_t devis_msda_kernel_launches(int family);
  * DEVIS_MSDA_ERR_UNSUPPORTED and every key stays at 0 = built-in heuristic.
  * key 0: forward threads per block, 1: forward queries per lane group,
  * key 2: backward threads per block, 3: backward queries per lane group,
- * key 4: 4-lane x 8-channel forward kernel: 0 = bf16 only (default), 1 = never, 2 = always,
- * key 5: 8-lane forward kernel with 16-byte tap records: 0 = fp32 only (default), 1 = always, 2 = never,
+ * keys 4, 5: unused since round 2 (they chose between forward kernels that no longer exist),
  * key 6: 1 = deterministic mode uses the direct 64-bit scatter instead of the sorted kernel,
  * key 7: sorted kernel's window margin in pixels (0 = 6), key 9: its first level with a window + 1. */
 int devis_msda_set_tuning(int key, int value);
