@@ -692,7 +692,7 @@ def run_ours(args, rank, world, local_rank):
             del ops
         except Exception as exc:   # noqa: BLE001 -- secondary rows must never take the headline down
             extra["error"] = str(exc)[:200]
-    fwd_kernel = "msda_fwdv_kernel" if dtype == torch.float32 else "msda_fwd8_kernel"   # what the launcher picks at D = 32
+    fwd_kernel = "msda_fwdv_kernel" if dtype == torch.float32 else "msda_fwd8v_kernel"   # what the launcher picks at D = 32
 
     # ---- the on-chip resources that actually bind: every tap gathers 4 value rows through the SM's
     # L1 data pipe (128 B/clk/SM), every live corner leaves the SM as one row reduction (cycles per 128-B row measured
