@@ -113,7 +113,7 @@ __device__ __forceinline__ void row_softmax_stats(const FusedArgs &a, size_t row
 }
 
 // raw operands of one tap as the Linear layers wrote them; loaded one exchange AHEAD of their use (like
-// msda_fwdc_kernel's load_taps) so that their DRAM latency hides under the 32 corner gathers of the exchange before
+// msda_fwdv_kernel's load_taps) so that their DRAM latency hides under the 32 corner gathers of the exchange before
 struct RawTap {
     float2 off;   // sampling offset (pixels of the tap's level; box form: in units of box size / (2 P))
     float4 rf;    // reference point (x, y) or box (x, y, w, h) the tap starts from
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256, DEVIS_FUSED_FWD_MIN_BLOCKS) tmsda_fused_f
     }
 }
 
-// Four lanes per (query, head), 8 channels per lane (msda_fwd8_kernel's shape): the forward of choice for bf16 value,
+// Four lanes per (query, head), 8 channels per lane (msda_fwd8v_kernel's shape): the forward of choice for bf16 value,
 // whose 64-byte rows cost 0.75 instead of 1.0 data-pipe cycles when 4 lanes fetch 16 bytes each.
 // bf16 value only (the fp32 form of this shape loses to the eight-lane kernel); dead corners skipped, consume_tap16x4v
 template <int ROWB>
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) tmsda_fused_fwd8_kernel(const FusedArgs a
             const int4 sl = s_slot[slot_base + div_p(k0, P, pshift)];
             const unsigned pitch = (unsigned)sl.y * rowbytes;
             // loaded at use: with 8 groups per warp a prefetch one exchange ahead does not pay here (531 vs 524 us; the
-            // same holds for msda_fwd8_kernel, 431 vs 403 us)
+            // same held for the unfused four-lane kernel, 431 vs 403 us)
             const RawTap cur = load_raw_tap<false>(a, sg, row, qrow, k, qlive);
             float x = 0.f, y = 0.f, w = 0.f;
             if (qlive) raw_to_operands<false>(a, sg, cur, sl, rmax, rinv, x, y, w);
