@@ -818,6 +818,29 @@ def run_ours(args, rank, world, local_rank):
             import traceback
             extra["train_trunk"] = {"error": str(exc)[:300], "where": traceback.format_exc()[-700:]}
 
+    # ---- BASELINE.json config 5 on the WHOLE model (every N): ResNet-50 + transformer + heads + mask head, forward + backward +
+    #      DDP gradient all-reduce + clip_grad_norm + AdamW, one synthetic clip per rank (benchmarks/devis_r50_inference.py)
+    if not args.only_headline and not args.no_train_trunk and dtype == torch.float32:
+        try:
+            torch.cuda.empty_cache()
+            from torch import nn as _nn
+            from benchmarks import devis_r50_inference
+            wrap = (lambda net: _nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], find_unused_parameters=True)) \
+                if world > 1 else None
+            r = devis_r50_inference.run_train("ours", iters=6, tf32=False, ddp=wrap)
+            ms = float(r["ours"]["ms_per_step"])
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+                ms = float(t.item())
+            extra["full_model_train"] = {"config": r["config"], "ms_per_step": ms, "clips_per_sec": world / (ms * 1e-3),
+                                         "params": r["ours"]["trainable_params"],
+                                         "allreduce_bytes_per_step": r["ours"]["trainable_params"] * 4 if world > 1 else 0,
+                                         "note": "max over ranks; at N = 1 the same step on the reference's ops takes 1.86x as long "
+                                                 "(profiles/r2ae_devis_r50_train_step.json)"}
+        except Exception as exc:   # noqa: BLE001
+            extra["full_model_train"] = {"error": str(exc)[:300]}
+
     # ---- BASELINE.json config 3: DeVIS R50 T=6 full-model inference (rank 0, one GPU's rate; benchmarks/devis_r50_inference.py)
     if rank == 0 and not args.only_headline and dtype == torch.float32:
         try:

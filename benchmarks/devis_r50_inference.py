@@ -1,6 +1,6 @@
 """BASELINE.json config 3: DeVIS R50 T=6 full-model INFERENCE on synthetic 360 x 640 clips, random-init weights, one B200.
 
-    python benchmarks/devis_r50_inference.py [--attn ours|reference|both] [--iters 20] [--num-out 20]
+    python benchmarks/devis_r50_inference.py [--attn ours|reference|both] [--iters 20] [--num-out 20] [--train]
 
 This is a BENCHMARK ASSEMBLY, not a product module: the hot path of this repository (temporal attention modules, mask-head
 deformable convolution) embedded in everything DeVIS runs around it at inference, so that the end-to-end effect of the
@@ -92,9 +92,7 @@ class DeVISR50(nn.Module):
         self.bbox_attention = segm.MultiScaleMHAttentionMap(hidden, hidden, 8, num_levels=3, dropout=0)
         self.mask_head = segm.MaskHeadConv(hidden, [hidden, hidden, chans[0]], 8, True, ["/32", "/16", "/8"], num_levels=4)
 
-    @torch.no_grad()
-    def forward(self, frames, pad_mask):
-        """frames (T, 3, H, W), pad_mask (T, H, W) bool -> (masks (n, T, H/4, W/4), scores, labels, boxes)"""
+    def trunk(self, frames, pad_mask):
         feats = [v for _, v in sorted(self.body(frames).items())]
         masks = [F.interpolate(pad_mask[None].float(), size=f.shape[-2:]).to(torch.bool)[0] for f in feats]
         srcs = [self.input_proj[i](f) for i, f in enumerate(feats[1:])]
@@ -102,6 +100,35 @@ class DeVISR50(nn.Module):
         lvl_masks = masks[1:] + [F.interpolate(pad_mask[None].float(), size=srcs[-1].shape[-2:]).to(torch.bool)[0]]
         pos = [sine_position(m) for m in lvl_masks]
         hs, _, memories, _, inter_refs, *_ = self.transformer(srcs, lvl_masks, pos, self.query_embed.weight)
+        return feats, lvl_masks, hs, memories, inter_refs
+
+    def masks_for(self, hs_f, feats, lvl_masks, memories, n):
+        """box attention maps and the convolutional mask head on /32, /16, /8 encoded + /4 backbone features"""
+        mem = [memories[i][0].transpose(0, 1) for i in (2, 1, 0)]
+        bbox_mask = self.bbox_attention(hs_f, mem, mask=[lvl_masks[i] for i in (2, 1, 0)])
+        bbox_mask = [b.transpose(1, 0).flatten(0, 1) for b in bbox_mask]
+        seg = self.mask_head(mem + [feats[0]], bbox_mask, instances_per_batch=n,
+                             expand_func=lambda t, k: t.repeat(k, 1, 1, 1))
+        return seg.view((n, self.n_frames) + seg.shape[2:])
+
+    def training_loss(self, frames, pad_mask, n_matched=5):
+        """BASELINE config 5's forward: every decoder level's class / box outputs (auxiliary losses) and the masks of
+        `n_matched` trajectories at the last level (DeVIS._training_forward with a fixed matching: the Hungarian matcher and
+        SetCriterion are CPU / out of scope, devis_segmentation.py:37-45,69-75); a synthetic quadratic loss stands in for
+        the criterion so that every parameter on the path gets a gradient."""
+        feats, lvl_masks, hs, memories, inter_refs = self.trunk(frames, pad_mask)
+        loss = frames.new_zeros(())
+        for lvl in range(hs.shape[0]):
+            loss = loss + self.class_embed[lvl](hs[lvl]).float().square().mean() + inter_refs[lvl].float().square().mean()
+        n_traj = self.n_queries // self.n_frames
+        hs_f = hs[-1][0].view(self.n_frames, n_traj, -1)[:, :n_matched]
+        seg = self.masks_for(hs_f, feats, lvl_masks, memories, n_matched)
+        return loss + seg.float().square().mean() + 1e-3 * sum(m.float().square().mean() for m in memories)
+
+    @torch.no_grad()
+    def forward(self, frames, pad_mask):
+        """frames (T, 3, H, W), pad_mask (T, H, W) bool -> (masks (n, T, H/4, W/4), scores, labels, boxes)"""
+        feats, lvl_masks, hs, memories, inter_refs = self.trunk(frames, pad_mask)
         logits = self.class_embed[-1](hs[-1])                         # (1, T * n_traj, classes + 1)
         boxes = inter_refs[-1]                                        # with_gradient: the refined boxes themselves
         # DeVISPostProcessor (focal loss): trajectory score = mean over frames, top-k over (trajectory, class)
@@ -114,13 +141,8 @@ class DeVISR50(nn.Module):
         uniq, inverse = torch.unique(traj_idx, return_inverse=True)   # host-visible size, as in the reference
         n = int(uniq.shape[0])
         hs_f = hs[-1][0].view(self.n_frames, n_traj, -1)[:, uniq]
-        # box attention maps and the convolutional mask head on /32, /16, /8 encoded + /4 backbone features
-        mem = [memories[i][0].transpose(0, 1) for i in (2, 1, 0)]
-        bbox_mask = self.bbox_attention(hs_f, mem, mask=[lvl_masks[i] for i in (2, 1, 0)])
-        bbox_mask = [b.transpose(1, 0).flatten(0, 1) for b in bbox_mask]
-        seg = self.mask_head(mem + [feats[0]], bbox_mask, instances_per_batch=n,
-                             expand_func=lambda t, k: t.repeat(k, 1, 1, 1))
-        return seg.view((n, self.n_frames) + seg.shape[2:]), scores, labels, boxes.view(self.n_frames, n_traj, 4)[:, uniq], inverse
+        seg = self.masks_for(hs_f, feats, lvl_masks, memories, n)
+        return seg, scores, labels, boxes.view(self.n_frames, n_traj, 4)[:, uniq], inverse
 
 
 def use_reference_ops(model):
@@ -199,6 +221,67 @@ def stage_breakdown(model, frames, pad):
     return {k: round(v / 3e3, 3) for k, v in fam.items()}      # ms per clip
 
 
+def run_train(attn="both", iters=8, height=360, width=640, tf32=False, ddp=None, n_matched=5):
+    """BASELINE config 5 on the whole model: forward (all decoder levels + masks of `n_matched` trajectories) + backward +
+    gradient all-reduce (when `ddp` wraps the model: pass a callable module -> DistributedDataParallel) + clip_grad_norm(0.1)
+    + AdamW, one synthetic clip per rank; returns ms per step (CUDA events, median)."""
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    out = {"config": "DeVIS R50 training step, T=6, %dx%d, 60 queries, 6+6 layers, 4+4 points, dropout 0.1, %d matched "
+                     "trajectories in the mask head, aux outputs of all decoder levels, synthetic quadratic loss, fp32 (TF32 %s), "
+                     "AdamW + clip_grad_norm 0.1" % (height, width, n_matched, "on" if tf32 else "off")}
+    frames = torch.randn(6, 3, height, width, device=dev)
+    pad = torch.zeros(6, height, width, dtype=torch.bool, device=dev)
+
+    def measure(model):
+        class Step(nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, x):
+                return self.m.training_loss(x, pad, n_matched)
+        net = Step(model)
+        runner = ddp(net) if ddp is not None else net
+        params = [p for p in net.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            runner(frames).backward()
+            torch.nn.utils.clip_grad_norm_(params, 0.1)
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in evs:
+            a.record()
+            step()
+            b.record()
+        torch.cuda.synchronize()
+        ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+        return {"ms_per_step": round(ms, 3), "clips_per_sec": round(1e3 / ms, 3), "iters": iters,
+                "trainable_params": sum(p.numel() for p in params)}
+
+    model = DeVISR50().to(dev).train()
+    for p in model.body.parameters():                     # the reference trains the backbone at lr 1e-5; kept trainable
+        p.requires_grad_(True)
+    if attn in ("ours", "both"):
+        out["ours"] = measure(model)
+    if attn in ("reference", "both"):
+        try:
+            use_reference_ops(model)
+            out["reference_ops"] = measure(model)
+            if "ours" in out:
+                out["speedup"] = round(out["reference_ops"]["ms_per_step"] / out["ours"]["ms_per_step"], 3)
+        except Exception as exc:  # noqa: BLE001
+            out["reference_ops"] = {"error": str(exc)[:300]}
+    return out
+
+
 def run(attn="both", iters=20, num_out=20, breakdown=True, height=360, width=640, tf32=False):
     """tf32: torch.backends.{cuda.matmul,cudnn}.allow_tf32 for everything dense (backbone, projections, FFN, mask-head
     GEMMs; the reference's pinned torch 1.11 had both on by default).  The attention kernels are fp32 either way."""
@@ -242,8 +325,12 @@ if __name__ == "__main__":
     ap.add_argument("--num-out", type=int, default=20)
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--tf32", default="both", choices=["off", "on", "both"])
+    ap.add_argument("--train", action="store_true", help="time the training step (config 5) instead of inference (config 3)")
     a = ap.parse_args()
     res = {}
     for mode in (["off", "on"] if a.tf32 == "both" else [a.tf32]):
-        res["tf32_" + mode] = run(a.attn, a.iters, a.num_out, not a.no_breakdown, tf32=mode == "on")
+        if a.train:
+            res["tf32_" + mode] = run_train(a.attn, max(4, a.iters // 3), tf32=mode == "on")
+        else:
+            res["tf32_" + mode] = run(a.attn, a.iters, a.num_out, not a.no_breakdown, tf32=mode == "on")
     print(json.dumps(res))
