@@ -1,7 +1,7 @@
 """Coarse performance guards at the DeVIS R50 T=6 encoder layer-clip (the bench.py workload): a kernel that silently
 falls off its launch shape or register budget (it happened: a launch-bounds hint made the bf16 forward 2x slower with
-every parity test green) fails here.  Bounds are ~25 % above the times measured on B200 (profiles/), far below a 2x
-regression; medians of 10 launches after warm-up, CUDA events."""
+every parity test green) fails here.  Bounds are 50 % above the times measured on B200 (profiles/) -- room for a slower-clocked box, still
+below a 2x regression; medians of 10 launches after warm-up, CUDA events."""
 import statistics
 
 import pytest
@@ -23,7 +23,7 @@ def _median_us(fn, n=10):
     return statistics.median(a.elapsed_time(b) for a, b in ev) * 1e3
 
 
-@pytest.mark.parametrize("dtype,fwd_bound,bwd_bound", [(torch.float32, 600.0, 1800.0), (torch.bfloat16, 470.0, 1750.0)])
+@pytest.mark.parametrize("dtype,fwd_bound,bwd_bound", [(torch.float32, 720.0, 2130.0), (torch.bfloat16, 540.0, 2080.0)])
 def test_whole_clip_kernels_stay_near_their_measured_times(dtype, fwd_bound, bwd_bound):
     if torch.cuda.get_device_properties(0).multi_processor_count < 140:
         pytest.skip("bounds are B200 numbers")
